@@ -1,0 +1,488 @@
+/*
+ * qmann_oracle.c -- CPU restatement of the reference CUDA forward (see qmann_oracle.h).
+ * TEST INFRASTRUCTURE ONLY; never linked into the product library.
+ *
+ * Style rule for this file: follow the reference macro expansion literally, including the
+ * C types it produces (CUDA_FLOAT_QUANT is a ternary between a double literal and a float, so
+ * its value is a double; products/sums of two FLOAT_QUANTs are therefore formed in double),
+ * and emulate the two device behaviours the host compiler does not give us:
+ *   - float/double -> int conversion saturates (cvt.rzi.s32), NaN -> 0
+ *   - no FMA contraction where the kernel round-trips through shared memory
+ * Build with -ffp-contract=off (oracle/Makefile does).
+ */
+#include "qmann_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* quantiser: lib/layer_cuda.h:207-253                                                        */
+/* ------------------------------------------------------------------------------------------ */
+
+/* device (int)x : cvt.rzi.s32.{f32,f64} -- truncates toward zero, saturates, NaN -> 0 */
+static inline int32_t dev_f2i(double x)
+{
+    if (x != x) return 0;
+    if (x >= 2147483647.0) return INT32_MAX;
+    if (x <= -2147483648.0) return INT32_MIN;
+    return (int32_t)x;
+}
+
+/* CUDA_FIXED_MAX_FIXED(iwl,frac) = (int)((unsigned int)(1<<(iwl+frac))-1)   layer_cuda.h:207 */
+static inline int32_t fixed_max_fixed(uint32_t iwl, uint32_t frac)
+{
+    return (int32_t)((uint32_t)(1u << ((iwl + frac) & 31u)) - 1u);
+}
+
+/* (1<<frac) as the int the macro produces (frac==31 wraps to INT_MIN on the device) */
+static inline int32_t one_shl(uint32_t frac) { return (int32_t)(1u << (frac & 31u)); }
+
+/* CUDA_FIXED_MAX_FLOAT = (float)((float)MAX_FIXED/(float)(1<<frac))         layer_cuda.h:210 */
+static inline float fixed_max_float(uint32_t iwl, uint32_t frac)
+{
+    return (float)((float)fixed_max_fixed(iwl, frac) / (float)one_shl(frac));
+}
+
+/* _CUDA_FLOAT2FIXED, the only compiled variant (EN_QUANT_MODE undefined)    layer_cuda.h:233 */
+static inline int32_t raw_float2fixed(double x, uint32_t iwl, uint32_t frac)
+{
+    const float maxf = fixed_max_float(iwl, frac);
+    const float minf = (float)(-1 * maxf);                   /* layer_cuda.h:211 */
+    if (x > maxf) return fixed_max_fixed(iwl, frac);
+    if (x < minf) return (int32_t)(-1 * fixed_max_fixed(iwl, frac));   /* layer_cuda.h:208 */
+    return dev_f2i(x * one_shl(frac));
+}
+
+/* CUDA_FLOAT2FIXED                                                           layer_cuda.h:246 */
+uint32_t qmo_float2fixed(double x, uint32_t iwl, uint32_t frac)
+{
+    const int32_t n = raw_float2fixed(x, iwl, frac);
+    if (x >= 0.0) return (uint32_t)n;                        /* n & 0x7FFFFFFFF, n >= 0 */
+    return ((uint32_t)(~n) + 1u) | 0x80000000u;
+}
+
+/* CUDA_FIXED2FLOAT                                                           layer_cuda.h:247 */
+float qmo_fixed2float(uint32_t code, uint32_t iwl, uint32_t frac)
+{
+    (void)iwl;
+    if ((code & 0x80000000u) == 0u)
+        return (float)((float)code / one_shl(frac));
+    const int32_t v = (int32_t)(~(code & 0x7FFFFFFFu) + 1u);
+    return (float)((float)v / one_shl(frac));
+}
+
+/* CUDA_FLOAT_QUANT                                                           layer_cuda.h:253 */
+double qmo_quant(double x, uint32_t iwl, uint32_t frac)
+{
+    if ((iwl + frac) == 0) return (x >= 0.0) ? 1.0 : -1.0;
+    return (double)qmo_fixed2float(qmo_float2fixed(x, iwl, frac), iwl, frac);
+}
+
+/* CUDA_FIXED_MUL(out,a,b,...)  out is a float lvalue                          layer_cuda.h:258 */
+float qmo_fixed_mul(float a, float b, uint32_t iwl_a, uint32_t frac_a, uint32_t iwl_b, uint32_t frac_b)
+{
+    return (float)qmo_quant(qmo_quant(a, iwl_a, frac_a) * qmo_quant(b, iwl_b, frac_b), iwl_a, frac_a);
+}
+
+/* CUDA_FIXED_ADD                                                              layer_cuda.h:257 */
+float qmo_fixed_add(float a, float b, uint32_t iwl_a, uint32_t frac_a, uint32_t iwl_b, uint32_t frac_b)
+{
+    return (float)qmo_quant(qmo_quant(a, iwl_a, frac_a) + qmo_quant(b, iwl_b, frac_b), iwl_a, frac_a);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* integer closed forms -- what the CUDA kernels compute                 */
+/* ------------------------------------------------------------------------------------------ */
+static inline int32_t iclamp(int64_t v, int32_t lim)
+{
+    return (int32_t)(v > lim ? lim : (v < -lim ? -lim : v));
+}
+static inline int64_t trunc0_shr(int64_t v, uint32_t sh)     /* v / 2^sh toward zero */
+{
+    return v >= 0 ? (v >> sh) : -((-v) >> sh);
+}
+
+int32_t qmo_int_quant(double x, uint32_t iwl, uint32_t frac)
+{
+    const uint32_t c = qmo_float2fixed(x, iwl, frac);
+    const int32_t mag = (int32_t)(c & 0x7FFFFFFFu);
+    return (c & 0x80000000u) ? -mag : mag;
+}
+
+int32_t qmo_int_requant(int32_t n, uint32_t frac_from, uint32_t iwl_to, uint32_t frac_to)
+{
+    const int32_t lim = fixed_max_fixed(iwl_to, frac_to);
+    int64_t v = n;
+    if (frac_to >= frac_from) v = v * ((int64_t)1 << (frac_to - frac_from));
+    else                      v = trunc0_shr(v, frac_from - frac_to);
+    return iclamp(v, lim);
+}
+
+int32_t qmo_int_mul(int32_t a, int32_t b, uint32_t iwl_a, uint32_t frac_a, uint32_t frac_b)
+{
+    return iclamp(trunc0_shr((int64_t)a * (int64_t)b, frac_b), fixed_max_fixed(iwl_a, frac_a));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* kernels                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+
+/* _cuda_mat_vec_product<<<dim_out,dim_in>>>                               layer_cuda.cu:49-83 */
+void qmo_mat_vec_product(const float *mat, const float *vec, float *out, uint32_t dim_out, uint32_t dim_in,
+                         int f_fixed, qmo_fmt fm, qmo_fmt fv)
+{
+    for (uint32_t i = 0; i < dim_out; i++) {
+        float sum = 0;
+        if (f_fixed) {
+            for (uint32_t j = 0; j < dim_in; j++) {
+                const float t = qmo_fixed_mul(mat[(size_t)i * dim_in + j], vec[j], fm.iwl, fm.frac, fv.iwl, fv.frac);
+                sum += t;
+            }
+            out[i] = (float)qmo_quant(sum, fm.iwl, fm.frac);
+        } else {
+            for (uint32_t j = 0; j < dim_in; j++) {
+                const float t = mat[(size_t)i * dim_in + j] * vec[j];  /* stored to shared: rounded to fp32 */
+                sum += t;
+            }
+            out[i] = sum;
+        }
+    }
+}
+
+/* _cuda_mat_mat_trans_product<<<rows*cols,dim_in>>>: out[r][c] = sum_t a[r][t]*b[c][t]
+ *                                                                        layer_cuda.cu:105-172 */
+void qmo_mat_mat_trans_product(const float *a, const float *b, float *out, uint32_t rows, uint32_t cols,
+                               uint32_t dim_in, int f_fixed, qmo_fmt fm, qmo_fmt fv, qmo_fmt fout)
+{
+    for (uint32_t r = 0; r < rows; r++)
+        for (uint32_t c = 0; c < cols; c++) {
+            float sum = 0;
+            const float *ar = a + (size_t)r * dim_in, *bc = b + (size_t)c * dim_in;
+            if (f_fixed) {
+                for (uint32_t t = 0; t < dim_in; t++) {
+                    /* all-zero operand short cut: FIXED_MUL(0,b)=+0 or -0, adds nothing */
+                    if (ar[t] == 0.0f) continue;
+                    sum += qmo_fixed_mul(ar[t], bc[t], fm.iwl, fm.frac, fv.iwl, fv.frac);
+                }
+                out[(size_t)r * cols + c] = (float)qmo_quant(sum, fout.iwl, fout.frac);
+            } else {
+                for (uint32_t t = 0; t < dim_in; t++) {
+                    const float p = ar[t] * bc[t];
+                    sum += p;
+                }
+                out[(size_t)r * cols + c] = sum;
+            }
+        }
+}
+
+/* _cuda_mat_trans_mat_product<<<d,S>>>(p, C, out, 1, d, ...): out[c] = sum_t p[t]*C[t][c]
+ *                                                    layer_cuda.cu:547-635, call site :2430 */
+void qmo_mat_trans_mat_product(const float *p, const float *Cm, float *out, uint32_t S, uint32_t d,
+                               int f_fixed, qmo_fmt f)
+{
+    for (uint32_t c = 0; c < d; c++) {
+        float sum = 0;
+        if (f_fixed) {
+            for (uint32_t t = 0; t < S; t++)
+                sum += qmo_fixed_mul(p[t], Cm[(size_t)t * d + c], f.iwl, f.frac, f.iwl, f.frac);
+            out[c] = (float)qmo_quant(sum, f.iwl, f.frac);
+        } else {
+            for (uint32_t t = 0; t < S; t++) {
+                const float x = p[t] * Cm[(size_t)t * d + c];
+                sum += x;
+            }
+            out[c] = sum;
+        }
+    }
+}
+
+/* _cuda_hamming_similarity(..., f_weighted=true)                        layer_cuda.cu:218-326 */
+static float hamming_similarity_w(uint32_t in_a, uint32_t in_b, uint32_t num_bit)
+{
+    float tmp_sim = 0.0f;
+    const int sign_a = ((in_a & 0x80000000u) == 0u) ? 1 : -1;
+    const int sign_b = ((in_b & 0x80000000u) == 0u) ? 1 : -1;
+    for (uint32_t i = 1; i < num_bit; i++)
+        if ((in_a & (0x80000000u >> i)) == (in_b & (0x80000000u >> i)))
+            tmp_sim += powf(2, (float)(int)(-(int)i));
+    return (sign_a == sign_b) ? tmp_sim : (float)(-1.0 * tmp_sim);
+}
+
+/* element transform of _cuda_approximate_attention                      layer_cuda.cu:384-428 */
+float qmo_appx_element(float m, float v, uint32_t iwl, uint32_t num_bit)
+{
+    const uint32_t frac = 32 - 1 - iwl;                      /* layer_cuda.cu:2515 */
+    uint32_t fm = qmo_float2fixed(m, iwl, frac);
+    uint32_t fv = qmo_float2fixed(v, iwl, frac);
+    const uint32_t sm = fm & 0x80000000u, sv = fv & 0x80000000u;
+    const uint32_t am = fm & 0x7FFFFFFFu, av = fv & 0x7FFFFFFFu;
+    const uint32_t amin = (am >= av) ? av : am;
+    if (sm == sv) {
+        fm = sm | (am - amin);
+        fv = sv | (av - amin);
+    } else if (am >= av) {
+        fm = sm | (am + amin);                               /* may carry into bit 31 */
+        fv = sv | 0u;
+    } else {
+        fm = sm | 0u;
+        fv = sv | (av + amin);
+    }
+    return hamming_similarity_w(fm, fv, num_bit);
+}
+
+/* _cuda_approximate_attention<<<S,d>>>                                   layer_cuda.cu:355-541 */
+void qmo_approximate_attention(const float *M, const float *u, float *out, uint32_t S, uint32_t d,
+                               uint32_t iwl, uint32_t num_bit, int32_t const_scale)
+{
+    const uint32_t frac = 32 - 1 - iwl;
+    const float scale = powf(2, (float)const_scale);
+    for (uint32_t r = 0; r < S; r++) {
+        float sum = 0;
+        for (uint32_t t = 0; t < d; t++) {
+            float tmp = qmo_appx_element(M[(size_t)r * d + t], u[t], iwl, num_bit) * scale;
+            tmp = (float)qmo_quant(tmp, iwl, frac);
+            sum += tmp;
+        }
+        out[r] = (float)qmo_quant(sum, iwl, frac);
+    }
+}
+
+/* tree of _cuda_max / _cuda_max_i: left operand wins only on strict '>'  layer_cuda.cu:1895-1939 */
+uint32_t qmo_argmax_last(const float *in, uint32_t dim)
+{
+    if (dim == 0) return 0;
+    uint32_t *ind = (uint32_t *)malloc(sizeof(uint32_t) * dim);
+    for (uint32_t i = 0; i < dim; i++) ind[i] = i;
+    for (uint32_t step = 1; step < dim; step *= 2)
+        for (uint32_t t = 0; t + step < dim; t += 2 * step)
+            if (!(in[ind[t]] > in[ind[t + step]])) ind[t] = ind[t + step];
+    const uint32_t r = ind[0];
+    free(ind);
+    return r;
+}
+
+/* _cuda_max + _cuda_softmax_fwd (f_shift_based=false)                  layer_cuda.cu:1969-2060 */
+void qmo_softmax(const float *in, float *out, uint32_t dim)
+{
+    if (dim == 0) return;
+    const float mx = in[qmo_argmax_last(in, dim)];
+    for (uint32_t i = 0; i < dim; i++) out[i] = expf(in[i] - mx);    /* device: __expf */
+    double total = 0.0;
+    for (uint32_t i = 0; i < dim; i++) total += out[i];
+    for (uint32_t i = 0; i < dim; i++) out[i] = (float)(out[i] / total);
+}
+
+/* _cuda_vec_vec_sum<<<1,dim>>>                                         layer_cuda.cu:1535-1542 */
+void qmo_vec_vec_sum(const float *a, const float *b, float *out, uint32_t dim, int f_fixed, qmo_fmt f)
+{
+    for (uint32_t i = 0; i < dim; i++)
+        out[i] = f_fixed ? qmo_fixed_add(a[i], b[i], f.iwl, f.frac, f.iwl, f.frac) : a[i] + b[i];
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* whole forward                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+
+/* How many attention weights of this hop could flip their Q(p) code if every exp() carried the
+ * worst-case difference between libm expf and the device's ex2.approx path.  0 => the
+ * fixed-point values downstream of this softmax are implementation-independent. */
+static uint32_t softmax_flip_risk(const float *s, const float *p, uint32_t S, qmo_fmt f)
+{
+    if (S == 0) return 0;
+    float mx = s[0];
+    for (uint32_t i = 1; i < S; i++) if (s[i] > mx) mx = s[i];
+    double tl = 0, th = 0;
+    for (uint32_t i = 0; i < S; i++) {
+        const float x = s[i] - mx;
+        const double e = expf(x);
+        const double del = (x == 0.0f) ? 0.0 : (3e-7 + 1.5e-7 * fabs((double)x));
+        tl += e * (1.0 - del);
+        th += e * (1.0 + del);
+    }
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < S; i++) {
+        const float x = s[i] - mx;
+        const double e = expf(x);
+        const double del = (x == 0.0f) ? 0.0 : (3e-7 + 1.5e-7 * fabs((double)x));
+        const float plo = (float)(e * (1.0 - del) / th), phi = (float)(e * (1.0 + del) / tl);
+        if (qmo_float2fixed(plo, f.iwl, f.frac) != qmo_float2fixed(phi, f.iwl, f.frac)) n++;
+        (void)p;
+    }
+    return n;
+}
+
+typedef struct {
+    float *u, *M, *C, *s, *p, *o, *g, *un, *z, *h;
+} story_ws;
+
+static void ws_alloc(story_ws *w, uint32_t S, uint32_t d, uint32_t V)
+{
+    w->u = (float *)malloc(sizeof(float) * d);
+    w->M = (float *)malloc(sizeof(float) * (size_t)(S ? S : 1) * d);
+    w->C = (float *)malloc(sizeof(float) * (size_t)(S ? S : 1) * d);
+    w->s = (float *)malloc(sizeof(float) * (S ? S : 1));
+    w->p = (float *)malloc(sizeof(float) * (S ? S : 1));
+    w->o = (float *)malloc(sizeof(float) * d);
+    w->g = (float *)malloc(sizeof(float) * d);
+    w->un = (float *)malloc(sizeof(float) * d);
+    w->z = (float *)malloc(sizeof(float) * V);
+    w->h = (float *)malloc(sizeof(float) * V);
+}
+static void ws_free(story_ws *w)
+{
+    free(w->u); free(w->M); free(w->C); free(w->s); free(w->p);
+    free(w->o); free(w->g); free(w->un); free(w->z); free(w->h);
+}
+
+int qmo_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* One story through the layer graph of MemN2N/MemN2N.c:2626-2697 (wiring :2410-2548). */
+static void forward_one(const qmo_model *md, const float *x, const float *q, uint32_t S, story_ws *w,
+                        qmo_dump *dp, uint32_t i_story, size_t sen_off, size_t sum_sen, uint32_t N,
+                        uint32_t *risk_out)
+{
+    const uint32_t V = md->V, d = md->d, H = md->H;
+    const int fx = (int)md->f_fixed;
+    uint32_t risk = 0;
+
+    /* emb_q: dense(V->d), in fmt = w fmt = hop-0 weight fmt                  MemN2N.c:826 */
+    qmo_mat_vec_product(md->B, q, w->u, d, V, fx, md->fmt_w[0], md->fmt_w[0]);
+    if (dp && dp->u0) memcpy(dp->u0 + (size_t)i_story * d, w->u, sizeof(float) * d);
+
+    for (uint32_t h = 0; h < H; h++) {
+        const qmo_fmt fw = md->fmt_w[h], fa = md->fmt_att[h], ff = md->fmt[h], fb = md->fmt_bin;
+        /* emb_m[h], emb_c[h]: dense_mat                                   MemN2N.c:835-838 */
+        qmo_mat_mat_trans_product(x, md->A[h], w->M, S, d, V, fx, fw, fw, fw);
+        qmo_mat_mat_trans_product(x, md->C[h], w->C, S, d, V, fx, fw, fw, fw);
+
+        /* dotmv[h]: addressing                       MemN2N.c:847-850, layer.c:176-252 */
+        if (md->mode == 3) {
+            /* cuda_dot_mat_vec_fwd_appx(..., iwl_m, frac_m, num_bit = 1+iwl_m+frac_m) */
+            qmo_approximate_attention(w->M, w->u, w->s, S, d, fa.iwl, 1 + fa.iwl + fa.frac, md->const_scale);
+        } else {
+            /* mode 2: vec fmt = bin; mode 1: f_fixed=false */
+            const int fxa = (md->mode == 2) ? 1 : 0;
+            qmo_mat_mat_trans_product(w->M, w->u, w->s, S, 1, d, fxa, fa, fb, fa);
+        }
+        /* sf_in[h]                                                          MemN2N.c:856 */
+        qmo_softmax(w->s, w->p, S);
+        if (md->mode != 1 && fx) risk += softmax_flip_risk(w->s, w->p, S, ff);
+
+        /* w_sum[h]: weighted read; mode 1 passes f_fixed=false, mode 2 true, mode 3 dot->f_fixed
+         *                                                     MemN2N.c:863, layer.c:176-233 */
+        {
+            const int fxr = (md->mode == 1) ? 0 : (md->mode == 2 ? 1 : fx);
+            qmo_mat_trans_mat_product(w->p, w->C, w->o, S, d, fxr, ff);
+        }
+        /* lin_map[h]: dense(d->d), in fmt = bin, w fmt = hop weight fmt         MemN2N.c:873 */
+        const float *a_in = w->u;
+        if (md->lin_map) {
+            qmo_mat_vec_product(md->Hm[h], w->u, w->g, d, d, fx, fw, fb);
+            a_in = w->g;
+        } else {
+            memcpy(w->g, w->u, sizeof(float) * d);
+        }
+        /* sv[h]: u_{h+1} = Q(Q(a)+Q(o))                                          MemN2N.c:889 */
+        qmo_vec_vec_sum(a_in, w->o, w->un, d, fx, ff);
+
+        if (dp) {
+            const size_t so = (size_t)h * sum_sen + sen_off;
+            if (dp->M) memcpy(dp->M + so * d, w->M, sizeof(float) * (size_t)S * d);
+            if (dp->C) memcpy(dp->C + so * d, w->C, sizeof(float) * (size_t)S * d);
+            if (dp->s) memcpy(dp->s + so, w->s, sizeof(float) * S);
+            if (dp->p) memcpy(dp->p + so, w->p, sizeof(float) * S);
+            const size_t vo = ((size_t)h * N + i_story) * d;
+            if (dp->o) memcpy(dp->o + vo, w->o, sizeof(float) * d);
+            if (dp->g) memcpy(dp->g + vo, w->g, sizeof(float) * d);
+            if (dp->u) memcpy(dp->u + vo, w->un, sizeof(float) * d);
+        }
+        memcpy(w->u, w->un, sizeof(float) * d);
+    }
+
+    /* ds_ans: dense(d->V), f_fixed=false                                 MemN2N.c:902-906 */
+    qmo_fmt none = {0, 0};
+    qmo_mat_vec_product(md->W, w->u, w->z, V, d, 0, none, none);
+    /* sf_out                                                               MemN2N.c:910 */
+    qmo_softmax(w->z, w->h, V);
+    *risk_out = risk;
+}
+
+uint32_t qmo_forward(const qmo_model *md, const float *m, const float *q, const float *a,
+                     const uint32_t *n_sen, uint32_t N, qmo_dump *dp, float *cost, int n_threads)
+{
+    const uint32_t V = md->V, d = md->d;
+    size_t *off = (size_t *)malloc(sizeof(size_t) * ((size_t)N + 1));
+    uint32_t Smax = 0;
+    off[0] = 0;
+    for (uint32_t i = 0; i < N; i++) {
+        off[i + 1] = off[i] + n_sen[i];
+        if (n_sen[i] > Smax) Smax = n_sen[i];
+    }
+    const size_t sum_sen = off[N];
+    uint32_t *pred = (uint32_t *)malloc(sizeof(uint32_t) * (N ? N : 1));
+    float *htrue = (float *)malloc(sizeof(float) * (N ? N : 1));
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+    n_threads = 1;
+#endif
+
+#pragma omp parallel num_threads(n_threads)
+    {
+        story_ws w;
+        ws_alloc(&w, Smax, d, V);
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t i = 0; i < (int64_t)N; i++) {
+            uint32_t risk = 0;
+            forward_one(md, m + off[i] * V, q + (size_t)i * V, n_sen[i], &w, dp, (uint32_t)i, off[i], sum_sen, N, &risk);
+            /* ce: pred = _cuda_max_i(h); cost += -h[y]; match += (pred==y)
+             *                                              layer_cuda.cu:1918-1939, 2191-2203 */
+            const uint32_t pi = qmo_argmax_last(w.h, V);
+            pred[i] = pi;
+            float ht = 0.0f;
+            if (a) for (uint32_t k = 0; k < V; k++) if (a[(size_t)i * V + k] == 1.0f) ht = w.h[k];
+            htrue[i] = ht;
+            if (dp) {
+                if (dp->z) memcpy(dp->z + (size_t)i * V, w.z, sizeof(float) * V);
+                if (dp->h) memcpy(dp->h + (size_t)i * V, w.h, sizeof(float) * V);
+                if (dp->pred) dp->pred[i] = pi;
+                if (dp->h_true) dp->h_true[i] = ht;
+                if (dp->risk) dp->risk[i] = (float)risk;
+                if (dp->risk_ans) {
+                    float top = w.h[pi], second = -1.0f;
+                    for (uint32_t k = 0; k < V; k++) if (k != pi && w.h[k] > second) second = w.h[k];
+                    dp->risk_ans[i] = (top > 0.0f && second >= 0.0f) ? (top - second) / top : 1.0f;
+                }
+            }
+        }
+        ws_free(&w);
+    }
+
+    uint32_t match = 0;
+    float c = cost ? *cost : 0.0f;
+    if (a) {
+        for (uint32_t i = 0; i < N; i++) {
+            /* one thread has y==1: *dev_cost += -1.0*h[y]; if (tid==*max_i) *m_cnt += 1 */
+            uint32_t yi = V;
+            for (uint32_t k = 0; k < V; k++) if (a[(size_t)i * V + k] == 1.0f) yi = k;
+            if (yi < V) {
+                c = (float)((double)c + -1.0 * (double)htrue[i]);
+                if (pred[i] == yi) match++;
+            }
+        }
+    }
+    if (cost) *cost = c;
+    free(off); free(pred); free(htrue);
+    return match;
+}
