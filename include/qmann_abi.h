@@ -1,0 +1,224 @@
+/*
+ * qmann_abi.h -- C ABI of libqmann_b200.so, the B200 (sm_100a) implementation of Q-MANN's
+ * quantized MemN2N inference forward.
+ *
+ * Part 1 re-declares the reference's `extern "C" void cuda_*` surface (lib/layer_cuda.cu:2296-4943).
+ *   The reference ships NO header for it: lib/layer.c and MemN2N/MemN2N.c call these through
+ *   implicit declarations (MemN2N/Makefile:16 `-w`).  libqmann_b200.so exports every symbol
+ *   with exactly the reference's parameter list, so the unmodified layer.o / MemN2N.o link
+ *   against it instead of layer_cuda.o.  Forward / lifetime / data entry
+ *   points are real; training entry points (`*_bwd`, `*_w_up`, ...) exist only to satisfy the
+ *   linker and abort with a message (training is out of scope).
+ *   Error convention is the reference's: void return, CUDA errors print
+ *   "[*E] CUDA : <fn> : <msg>" to stderr and exit(code)          (lib/layer_cuda.h:13-22).
+ *
+ * Part 2 is the batched entry the reference does not have: one call runs the whole forward of
+ *   N stories (MemN2N/MemN2N.c:2377-2703 is one story per 31 launches).  It takes the same
+ *   device tensors the reference's layer structs own (fp32 weights, dense fp32 BoW arenas).
+ *   These return 0 on success or a negative QMANN_E_* code; qmann_last_error() has the text.
+ *
+ * All pointers named dev_* are CUDA device pointers; everything else is host memory.
+ * No C++ or torch types appear in any signature.
+ */
+#ifndef QMANN_ABI_H
+#define QMANN_ABI_H
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ============================================================================================
+ * Part 1 -- the reference's cuda_* surface.  "ref:" = definition line in lib/layer_cuda.cu.
+ * ========================================================================================== */
+
+/* ---- dot_mat_vec (addressing + weighted read) ------------------------------------------- */
+void cuda_dot_mat_vec_constructor(float **dev_out_vec, float **dev_grad_out_vec, float **dev_grad_out_mat, float **dev_f_overflow, float **dev_cliff_marker, unsigned int dim_mat_r, unsigned int dim_mat_c, bool f_trans);                                           /* ref: 2297 */
+void cuda_dot_mat_vec_init(float *dev_out_vec, float *dev_grad_out_vec, float *dev_grad_out_mat, float *dev_f_overflow, float *dev_cliff_marker, unsigned int dim_mat_r, unsigned int dim_mat_c, bool f_trans);                                                       /* ref: 2365 */
+void cuda_dot_mat_vec_fwd(float *dev_in_mat, float *dev_in_vec, float *dev_out_vec, float *dev_f_overflow, unsigned int dim_mat_r, unsigned int dim_mat_c, bool f_trans, bool f_fixed, unsigned int iwl_m, unsigned int frac_m, unsigned int iwl_v, unsigned int frac_v, unsigned int f_mode, bool verbose);   /* ref: 2406 */
+void cuda_dot_mat_vec_fwd_appx(float *dev_in_mat, float *dev_in_vec, float *dev_out_vec, float *dev_f_overflow, float *dev_cliff_marker, unsigned int dim_mat_r, unsigned int dim_mat_c, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode, unsigned int num_bit_attention, bool f_trans, bool verbose);   /* ref: 2491 */
+void cuda_dot_mat_vec_bwd(float *dev_in_mat, float *dev_in_vec, float *dev_grad_in, float *dev_grad_out_mat, float *dev_grad_out_vec, float *dev_f_overflow, unsigned int dim_mat_r, unsigned int dim_mat_c, bool f_trans, bool f_fixed, unsigned int iwl_m, unsigned int frac_m, unsigned int iwl_v, unsigned int frac_v, unsigned int f_mode, bool verbose);   /* ref: 2561, training */
+void cuda_dot_mat_vec_bwd_appx(float *dev_in_mat, float *dev_in_vec, float *dev_grad_in, float *dev_grad_out_mat, float *dev_grad_out_vec, float *dev_f_overflow, float *dev_cliff_marker, unsigned int dim_mat_r, unsigned int dim_mat_c, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode, unsigned int num_bit_attention, bool f_trans, bool verbose, unsigned int hop);   /* ref: 2667, training */
+void cuda_dot_mat_vec_destructor(float *dev_out_vec, float *dev_grad_out_vec, float *dev_grad_out_mat, float *dev_f_overflow, float *dev_cliff_marker);   /* ref: 2770 */
+
+/* ---- softmax ---------------------------------------------------------------------------- */
+void cuda_softmax_constructor(float **dev_out_vec, float **dev_grad_out, float **dev_max, unsigned int dim);   /* ref: 2792 */
+void cuda_softmax_init(float *dev_out_vec, float *dev_grad_out, float *dev_max, unsigned int dim);              /* ref: 2820 */
+void cuda_softmax_fwd(float *dev_out_vec, float *dev_in_vec, float *out_vec, float *in_vec, float *dev_max, unsigned int dim, bool f_shift_based, bool verbose);   /* ref: 2845 */
+void cuda_softmax_bwd(float *dev_grad_in, float *dev_out_vec, float *dev_grad_out, float *dev_in_vec, unsigned int dim, bool f_shift_based, bool verbose);         /* ref: 2886, training */
+void cuda_softmax_destructor(float *dev_out_vec, float *dev_grad_out, float *dev_max);                          /* ref: 2924 */
+
+/* ---- sum_vec (hop update) --------------------------------------------------------------- */
+void cuda_sum_vec_constructor(float **dev_out_vec, float **dev_grad_out, unsigned int dim);   /* ref: 2942 */
+void cuda_sum_vec_init(float *dev_out_vec, float *dev_grad_out, unsigned int dim);             /* ref: 2969 */
+void cuda_sum_vec_fwd(float *dev_in_vec_a, float *dev_in_vec_b, float *dev_out_vec, unsigned int dim, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode, bool verbose);   /* ref: 2992 */
+void cuda_sum_vec_bwd(float *dev_grad_out, float *dev_grad_in, float *grad_in, float *grad_out, unsigned int dim);   /* ref: 3032, training */
+void cuda_sum_vec_destructor(float *dev_out_vec, float *dev_grad_out);                         /* ref: 3064 */
+
+/* ---- dense (question embedding B, linear mapping H, answer projection W) ---------------- */
+void cuda_dense_constructor(float **dev_w_mat, float **dev_w_mat_del, float **dev_w_mat_best, float **dev_bias, float **dev_bias_del, float **dev_out_vec, float **dev_grad_out, float **dev_grad_l2_norm, float **dev_grad_bias_l2_norm, float **dev_f_overflow, unsigned int dim_in, unsigned int dim_out);   /* ref: 3080 */
+void cuda_dense_init(float *dev_out_vec, float *dev_grad_out, float *dev_w_mat_del, float *dev_w_mat, float *dev_bias, float *dev_bias_del, float *w_mat, float *bias, float *dev_f_overflow, unsigned int dim_in, unsigned int dim_out);   /* ref: 3126 */
+void cuda_dense_fwd(float *dev_w_mat, float *dev_bias, float *dev_in_vec, float *dev_out_vec, float *dev_f_overflow, unsigned int dim_in, unsigned int dim_out, char *activation, bool f_fixed, unsigned int iwl_in, unsigned int frac_in, unsigned int iwl_w, unsigned int frac_w, unsigned int f_mode, bool verbose);   /* ref: 3163 */
+void cuda_dense_bwd(float *dev_w_mat, float *dev_w_mat_del, float *dev_bias, float *dev_bias_del, float *dev_in_vec, float *dev_out_vec, float *dev_grad_in, float *dev_grad_out, float *dev_f_overflow, unsigned int dim_in, unsigned int dim_out, char *activation, bool f_fixed, unsigned int iwl_in, unsigned int frac_in, unsigned int iwl_w, unsigned int frac_w, unsigned int f_mode, bool verbose);   /* ref: 3233, training */
+void cuda_dense_w_up(float *dev_w_mat, float *dev_w_mat_del, float *dev_bias, float *dev_bias_del, float *dev_grad_l2_norm, float *dev_grad_bias_l2_norm, unsigned int dim_in, unsigned int dim_out, unsigned int batch_size, float *lr, float *lambda, float *max_grad_l2_norm, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode, bool verbose);   /* ref: 3318, training */
+void cuda_dense_destructor(float *dev_w_mat, float *dev_w_mat_del, float *dev_w_mat_best, float *dev_out_vec, float *dev_grad_out, float *dev_grad_l2_norm, float *dev_grad_bias_l2_norm, float *dev_f_overflow);   /* ref: 3366 */
+void cuda_dense_test_dtoh(float *dev_in_vec, float *in_vec, unsigned int dim_in, unsigned int dim_out);   /* ref: 3390 */
+void cuda_dense_test_htod(float *dev_in_vec, float *in_vec, unsigned int dim_in, unsigned int dim_out);   /* ref: 3402 */
+
+/* ---- dense_mat (memory embeddings A / C incl. temporal-encoding columns) ----------------- */
+void cuda_dense_mat_constructor(float **dev_w_mat, float **dev_w_mat_del, float **dev_w_mat_best, float **dev_bias, float **dev_bias_del, float **dev_out_mat, float **dev_grad_out, float **dev_grad_l2_norm, float **dev_grad_bias_l2_norm, float **dev_f_overflow, unsigned int dim_in, unsigned int dim_out, unsigned int dim_len);   /* ref: 3418 */
+void cuda_dense_mat_init(float *dev_out_mat, float *dev_grad_out, float *dev_w_mat, float *dev_w_mat_del, float *dev_bias, float *dev_bias_del, float *w_mat, float *bias, float *dev_f_overflow, unsigned int dim_in, unsigned int dim_out, unsigned int dim_len);   /* ref: 3469 */
+void cuda_dense_mat_fwd(float *dev_w_mat, float *dev_bias, float *dev_in_mat, float *dev_out_mat, float *dev_f_overflow, unsigned int dim_in, unsigned int dim_out, unsigned int dim_len, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode, bool verbose);   /* ref: 3512 */
+void cuda_dense_mat_bwd(float *dev_in_mat, float *dev_w_mat, float *dev_w_mat_del, float *dev_bias, float *dev_bias_del, float *dev_grad_in, float *dev_grad_out, float *dev_f_overflow, unsigned int dim_in, unsigned int dim_out, unsigned int dim_len, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode, bool verbose);   /* ref: 3571, training */
+void cuda_dense_mat_w_up(float *dev_w_mat, float *dev_w_mat_del, float *dev_bias, float *dev_bias_del, float *dev_grad_l2_norm, float *dev_grad_bias_l2_norm, float *w_mat, float *w_mat_del, unsigned int dim_in, unsigned int dim_out, unsigned int batch_size, float *lr, float *lambda, float *max_grad_l2_norm, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode, bool verbose);   /* ref: 3613, training */
+void cuda_dense_mat_destructor(float *dev_w_mat, float *dev_w_mat_del, float *dev_w_mat_best, float *dev_out_mat, float *dev_grad_out, float *dev_grad_l2_norm, float *dev_f_overflow);   /* ref: 3654 */
+
+/* ---- cross_entropy (prediction, cost, match count) -------------------------------------- */
+void cuda_cross_entropy_constructor(float **dev_cost_train, float **dev_cost_valid, float **dev_cost_test, unsigned int **dev_m_cnt_train, unsigned int **dev_m_cnt_valid, unsigned int **dev_m_cnt_test, unsigned int **dev_pred_i, float **dev_grad_out, unsigned int dim);   /* ref: 3680 */
+void cuda_cross_entropy_init(float *dev_cost_train, float *dev_cost_valid, float *dev_cost_test, unsigned int *dev_m_cnt_train, unsigned int *dev_m_cnt_valid, unsigned int *dev_m_cnt_test, float *dev_grad_out, unsigned int dim);   /* ref: 3717 */
+void cuda_cross_entropy_run(float *dev_cost_train, float *dev_cost_valid, float *dev_cost_test, unsigned int *dev_m_cnt_train, unsigned int *dev_m_cnt_valid, unsigned int *dev_m_cnt_test, unsigned int *dev_pred_i, float *cost, float *dev_h, float *dev_y, float *h, float *y, float *dev_grad_out, float *grad_out, unsigned int dim, unsigned int mode);   /* ref: 3750 */
+void cuda_cross_entropy_cost_load(float *dev_cost_train, float *dev_cost_valid, float *dev_cost_test, float *cost_train, float *cost_valid, float *cost_test);   /* ref: 3813 */
+void cuda_cross_entropy_m_cnt_load(unsigned int *dev_m_cnt_train, unsigned int *dev_m_cnt_valid, unsigned int *dev_m_cnt_test, unsigned int *m_cnt_train, unsigned int *m_cnt_valid, unsigned int *m_cnt_test);   /* ref: 3833 */
+void cuda_cross_entropy_destructor(float *dev_cost_train, float *dev_cost_valid, float *dev_cost_test, float *dev_m_cnt_train, float *dev_m_cnt_valid, float *dev_m_cnt_test, float *dev_pred_i, float *dev_grad_out);   /* ref: 3854 */
+
+/* ---- residual-gradient buffers (allocated unconditionally by MemN2N.c:977-984) ---------- */
+void cuda_dup_grad_constructor(float **dev_dup_grad, unsigned int num_hop, unsigned int dim);   /* ref: 3885 */
+void cuda_dup_grad_bwd(float *dev_dup_grad, float *dotmv_dev_grad_out_vec, float *sv_dev_grad_out_vec, float *dup_grad, unsigned int dim, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode);   /* ref: 3909, training */
+void cuda_dup_grad_destructor(float *dev_dup_grad);                                             /* ref: 3949 */
+
+/* ---- data arenas (one H2D of a whole split, MemN2N.c:2294-2350) -------------------------- */
+void cuda_data_constructor(float **dev_m, float **dev_q, float **dev_a, unsigned int dim_len, unsigned int dim_in, unsigned int num_sample);   /* ref: 3960 */
+void cuda_data_in(float *dev_m, float *dev_q, float *dev_a, float *m, float *q, float *a, unsigned int dim_len, unsigned int dim_in, unsigned int num_sample);   /* ref: 3991 */
+void cuda_data_destructor(float *dev_m, float *dev_q, float *dev_a);                           /* ref: 4023 */
+
+/* ---- matrix utilities -------------------------------------------------------------------- */
+void cuda_copy_mat(float *dev_src, float *dev_dest, unsigned int dim_col, unsigned int dim_row, bool f_trans);    /* ref: 4117 */
+void cuda_accum_mat(float *dev_src, float *dev_dest, unsigned int dim_col, unsigned int dim_row, bool f_trans);   /* ref: 4153, training */
+void cuda_set_value(float *dest, float value, unsigned int dim, unsigned int start_idx, unsigned int stride);     /* ref: 4646 */
+void cuda_memcpy_dev_to_host(float *host, float *dev, unsigned int size);                                         /* ref: 4436 */
+void cuda_copy_dev2host(float *host, float *dev, unsigned int size);                                              /* ref: 4932 */
+void cuda_binarization(float *dev_in_vec, unsigned int size);                                                     /* ref: 4454 */
+void cuda_quantization(float *dev_in_vec, unsigned int size, unsigned int iwl, unsigned int frac, unsigned int f_mode);   /* ref: 4476 */
+
+/* ---- element-wise product layers (never instantiated by MemN2N.c; link-only) ------------ */
+void cuda_mult_e_vec_constructor(float **dev_out_vec, float **dev_grad_out_a, float **dev_grad_out_b, unsigned int dim);   /* ref: 4176 */
+void cuda_mult_e_vec_init(float *dev_out_vec, float *dev_grad_out_a, float *dev_grad_out_b, unsigned int dim);             /* ref: 4205 */
+void cuda_mult_e_vec_fwd(float *dev_in_vec_a, float *dev_in_vec_b, float *dev_out_vec, float *in_vec_a, float *in_vec_b, float *out_vec, unsigned int dim);   /* ref: 4234 */
+void cuda_mult_e_vec_bwd(float *dev_in_vec_a, float *dev_in_vec_b, float *dev_grad_out_a, float *dev_grad_out_b, float *dev_grad_in, float *grad_in, float *grad_out_a, float *grad_out_b, unsigned int dim);   /* ref: 4266 */
+void cuda_mult_e_vec_destructor(void);                                                                                    /* ref: 4302 */
+void cuda_mult_e_mat_constructor(float **dev_out_mat, float **dev_grad_out_a, float **dev_grad_out_b, unsigned int dim_row, unsigned int dim_col);   /* ref: 4313 */
+void cuda_mult_e_mat_init(float *dev_out_mat, float *dev_grad_out_a, float *dev_grad_out_b, unsigned int dim_row, unsigned int dim_col);             /* ref: 4343 */
+void cuda_mult_e_mat_fwd(float *dev_in_mat_a, float *dev_in_mat_b, float *dev_out_mat, float *in_mat_a, float *in_mat_b, float *out_mat, unsigned int dim_row, unsigned int dim_col);   /* ref: 4373 */
+void cuda_mult_e_mat_bwd(float *dev_in_mat_a, float *dev_in_mat_b, float *dev_grad_out_a, float *dev_grad_out_b, float *dev_grad_in, float *grad_in, float *grad_out_a, float *grad_out_b, unsigned int dim_row, unsigned int dim_col);   /* ref: 4397 */
+void cuda_mult_e_mat_destructor(void);                                                                                    /* ref: 4428 */
+
+/* ---- optional forward layers, default off (EN_NON_LINEARITY, EN_SC_ATT) ------------------ */
+void cuda_activation_constructor(float **dev_out, float **dev_grad_out, unsigned int dim);   /* ref: 4504 */
+void cuda_activation_init(float *dev_out, float *dev_grad_out, unsigned int dim);             /* ref: 4528 */
+void cuda_activation_fwd(float *dev_in, float *dev_out, char *type_act, unsigned int dim, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode);   /* ref: 4548 */
+void cuda_activation_bwd(float *dev_out, float *dev_grad_in, float *dev_grad_out, char *type_act, unsigned int dim, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode);   /* ref: 4587, training */
+void cuda_activation_destructor(float *dev_out, float *dev_grad_out);                         /* ref: 4617 */
+void cuda_scale_constructor(float **dev_w, float **dev_w_del, float **dev_w_best, float **dev_out, float **dev_grad_out, unsigned int dim);   /* ref: 4748 */
+void cuda_scale_init(float *dev_w, float *dev_w_del, float *dev_out, float *dev_grad_out, float *w, unsigned int dim);                       /* ref: 4778 */
+void cuda_scale_fwd(float *dev_in, float *dev_w, float *dev_out, unsigned int dim, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode, bool verbose);   /* ref: 4805 */
+void cuda_scale_bwd(float *dev_in, float *dev_grad_in, float *dev_w, float *dev_w_del, float *dev_grad_out, unsigned int dim, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode, bool verbose);   /* ref: 4830, training */
+void cuda_scale_w_up(float *dev_w, float *dev_w_del, unsigned int dim, unsigned int batch_size, float *lr, float *lambda, bool f_fixed, unsigned int iwl, unsigned int frac, unsigned int f_mode, bool verbose);   /* ref: 4861, training */
+void cuda_scale_destructor(float *dev_w, float *dev_w_del, float *dev_w_best, float *dev_out, float *dev_grad_out);   /* ref: 4911 */
+
+/* ============================================================================================
+ * Part 2 -- batched forward (new).  Replaces the host loop MemN2N/MemN2N.c:2377-2703.
+ * ========================================================================================== */
+
+#define QMANN_MAX_HOP 8
+
+enum {
+    QMANN_OK = 0,
+    QMANN_E_ARG = -1,        /* bad argument / unsupported configuration            */
+    QMANN_E_CUDA = -2,       /* a CUDA runtime call failed                          */
+    QMANN_E_NOMEM = -3,      /* configuration does not fit the SM's shared memory   */
+};
+
+/* Compile-time configuration of the reference (MemN2N/define.h) + argv-derived formats
+ * (MemN2N/MemN2N.c:714-775), made run-time. */
+typedef struct {
+    uint32_t V;                       /* dim_input  (dictionary + time columns)      MemN2N.c:566-582 */
+    uint32_t d;                       /* dim_emb                                     define.h:159     */
+    uint32_t S_max;                   /* max_line   (memory slots)                   define.h:154     */
+    uint32_t H;                       /* NUM_HOP                                     define.h:254     */
+    uint32_t mode;                    /* ATTENTION_MODE 2 (fixed dot) | 3 (Hamming)  define.h:15      */
+    uint32_t lin_map;                 /* EN_LINEAR_MAPPING                           define.h:291     */
+    int32_t  const_scale;             /* ATTENTION_CONST_SCALE (mode 3)              define.h:67      */
+    uint32_t iwl[QMANN_MAX_HOP], frac[QMANN_MAX_HOP];           /* read + update     MemN2N.c:714-716 */
+    uint32_t iwl_w[QMANN_MAX_HOP], frac_w[QMANN_MAX_HOP];       /* weight layers     MemN2N.c:718-754 */
+    uint32_t iwl_att[QMANN_MAX_HOP], frac_att[QMANN_MAX_HOP];   /* addressing        MemN2N.c:721-722 */
+    uint32_t iwl_bin, frac_bin;                                 /* u operand         MemN2N.c:767-773 */
+} qmann_config;
+
+/* Device pointers to the fp32 weights as they live in the reference's layer structs
+ * (dense.dev_w_mat / dense_mat.dev_w_mat), row-major [dim_out][dim_in]. */
+typedef struct {
+    const float *dev_B;                       /* emb_q      [d][V]   MemN2N.c:826 */
+    const float *dev_A[QMANN_MAX_HOP];        /* emb_m[h]   [d][V]   MemN2N.c:835 */
+    const float *dev_C[QMANN_MAX_HOP];        /* emb_c[h]   [d][V]   MemN2N.c:838 */
+    const float *dev_Hm[QMANN_MAX_HOP];       /* lin_map[h] [d][d]   MemN2N.c:873 (NULL if !lin_map) */
+    const float *dev_W;                       /* ds_ans     [V][d]   MemN2N.c:906 */
+} qmann_weights;
+
+/* Optional per-story intermediates for parity checks (any member may be NULL).  fp32, same
+ * values the reference's layers would hold; ragged tensors are packed by sentence offset. */
+typedef struct {
+    float *dev_u0;     /* [N][d]            */
+    float *dev_M;      /* [H][sum_sen][d]   */
+    float *dev_C;      /* [H][sum_sen][d]   */
+    float *dev_s;      /* [H][sum_sen]      */
+    float *dev_p;      /* [H][sum_sen]      */
+    float *dev_o;      /* [H][N][d]         */
+    float *dev_g;      /* [H][N][d]         */
+    float *dev_u;      /* [H][N][d]         */
+    float *dev_z;      /* [N][V]            */
+    float *dev_h;      /* [N][V]            */
+} qmann_debug;
+
+typedef struct qmann_model qmann_model;   /* quantised weight images resident in HBM */
+typedef struct qmann_batch qmann_batch;   /* per-story sentence counts / offsets on the device */
+
+/* Quantise the fp32 weights into per-hop int8 images (device) and size the kernels.
+ * The model is bound to the CUDA device that is current at the time of the call. */
+int  qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_weights *w);
+void qmann_model_destroy(qmann_model *m);
+
+/* Describe a packed batch: n_sen[i] sentences for story i (host array, like n_sen_test_arr,
+ * MemN2N.c:2294-2333).  Uploads the offsets once. */
+int  qmann_batch_create(qmann_batch **out, const uint32_t *n_sen, uint32_t N);
+void qmann_batch_destroy(qmann_batch *b);
+
+/* Forward of all N stories on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ * dev_m [sum_sen][V], dev_q [N][V]: the arenas cuda_data_in() fills.  dev_a [N][V] one-hot or NULL.
+ * Outputs (device; any may be NULL): dev_pred[N] predicted answer index (argmax with the
+ * reference's last-index tie-break), dev_h_true[N] = h[y] (needs dev_a), *dev_match += #(pred==y).
+ * Asynchronous; returns after the launches are enqueued. */
+int  qmann_forward_batch(qmann_model *m, const qmann_batch *b, const float *dev_m, const float *dev_q,
+                         const float *dev_a, uint32_t *dev_pred, float *dev_h_true, uint32_t *dev_match,
+                         const qmann_debug *dbg, void *stream);
+
+/* End-to-end convenience over HOST arenas (pinned or pageable): chunked H2D copies overlapped
+ * with the forward, predictions copied back.  Returns the match count through *match (if a). */
+int  qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, const float *a_host,
+                      const uint32_t *n_sen, uint32_t N, uint32_t *pred_host, uint32_t *match, float *cost);
+
+/* Contiguous story range [first, first+count) for `rank` of `world`, balanced by sentence count
+ * (batch sharding across GPUs: stories are independent, no collective). */
+int  qmann_shard_plan(const uint32_t *n_sen, uint32_t N, uint32_t world, uint32_t rank,
+                      uint32_t *first, uint32_t *count);
+
+/* Number of kernel launches issued by this library since load (for benchmarks' accounting). */
+uint64_t qmann_launch_count(void);
+const char *qmann_last_error(void);
+const char *qmann_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMANN_ABI_H */

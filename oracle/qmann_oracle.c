@@ -225,11 +225,16 @@ float qmo_appx_element(float m, float v, uint32_t iwl, uint32_t num_bit)
         fm = sm | (am - amin);
         fv = sv | (av - amin);
     } else if (am >= av) {
-        fm = sm | (am + amin);                               /* may carry into bit 31 */
+        /* source: sign|(abs+min) on ints.  abs+min can reach 2^31: signed overflow is undefined
+         * behaviour, and nvcc 12.9 -arch=sm_100a folds the OR into one three-input add
+         * (IADD3 R3 = sign + min + abs, cuobjdump of oracle/_ref/layer_cuda.o @0x0c70), so a
+         * carry out of bit 30 CLEARS a set sign bit instead of leaving it set.  The compiled
+         * reference is the norm (tests/golden/kat_appx_element.npz pins it). */
+        fm = sm + am + amin;
         fv = sv | 0u;
     } else {
         fm = sm | 0u;
-        fv = sv | (av + amin);
+        fv = sv + av + amin;
     }
     return hamming_similarity_w(fm, fv, num_bit);
 }

@@ -142,6 +142,13 @@ int main(int argc, char **argv)
     float *o_z = falloc((size_t)N * V), *o_h = falloc((size_t)N * V);
     uint32_t *o_pred = (uint32_t *)calloc(N ? N : 1, 4);
 
+    /* The GPU path never reads the host-side tensors, but softmax_fwd loads in_vec[0] before
+     * dispatching (lib/layer.c:1163); hand every *_in() a valid dummy instead of NULL. */
+    const size_t dummy_n = (size_t)(V > d ? V : d) > S_max ? (size_t)(V > d ? V : d) : S_max;
+    float *hv = falloc(dummy_n);
+    float **hm = (float **)calloc(S_max ? S_max : 1, sizeof(float *));
+    for (uint32_t r = 0; r < S_max; r++) hm[r] = hv;
+
     const int passes = 1 + (time_reps > 0 ? time_reps : 0);
     double t_acc = 0.0;
     for (int pass = 0; pass < passes; pass++) {
@@ -151,26 +158,26 @@ int main(int argc, char **argv)
         size_t addr_m = 0;
         for (uint32_t i = 0; i < N; i++) {
             const uint32_t ns = n_sen[i];
-            /* wiring: MemN2N.c:2410-2548 (host pointers are unused by the GPU path: pass NULL) */
-            dense_in(&emb_q, NULL, NULL, dev_q + (size_t)i * V, NULL);
+            /* wiring: MemN2N.c:2410-2548 (host tensors are unused by the GPU path: dummies) */
+            dense_in(&emb_q, hv, hv, dev_q + (size_t)i * V, NULL);
             float *dev_u = emb_q.dev_out_vec;
             for (uint32_t h = 0; h < H; h++) {
-                dense_mat_in(&emb_m[h], ns, NULL, NULL, dev_m + addr_m * V, NULL);
-                dense_mat_in(&emb_c[h], ns, NULL, NULL, dev_m + addr_m * V, NULL);
-                dot_mat_vec_in(&dotmv[h], ns, NULL, NULL, NULL, emb_m[h].dev_out_mat, dev_u, NULL);
-                softmax_in(&sf_in[h], ns, NULL, NULL, dotmv[h].dev_out_vec, NULL);
-                dot_mat_vec_in(&w_sum[h], ns, NULL, NULL, NULL, emb_c[h].dev_out_mat, sf_in[h].dev_out_vec, NULL);
+                dense_mat_in(&emb_m[h], ns, hm, hm, dev_m + addr_m * V, NULL);
+                dense_mat_in(&emb_c[h], ns, hm, hm, dev_m + addr_m * V, NULL);
+                dot_mat_vec_in(&dotmv[h], ns, hm, hv, hv, emb_m[h].dev_out_mat, dev_u, NULL);
+                softmax_in(&sf_in[h], ns, hv, hv, dotmv[h].dev_out_vec, NULL);
+                dot_mat_vec_in(&w_sum[h], ns, hm, hv, hv, emb_c[h].dev_out_mat, sf_in[h].dev_out_vec, NULL);
                 float *dev_a_in = dev_u;
                 if (lin_map) {
-                    dense_in(&lin[h], NULL, NULL, dev_u, NULL);
+                    dense_in(&lin[h], hv, hv, dev_u, NULL);
                     dev_a_in = lin[h].dev_out_vec;
                 }
-                sum_vec_in(&sv[h], NULL, NULL, NULL, dev_a_in, w_sum[h].dev_out_vec, NULL);
+                sum_vec_in(&sv[h], hv, hv, hv, dev_a_in, w_sum[h].dev_out_vec, NULL);
                 dev_u = sv[h].dev_out_vec;
             }
-            dense_in(&ds_ans, NULL, NULL, dev_u, NULL);
-            softmax_in(&sf_out, V, NULL, NULL, ds_ans.dev_out_vec, NULL);
-            cross_entropy_in(&ce, NULL, NULL, sf_out.dev_out_vec, dev_a + (size_t)i * V);
+            dense_in(&ds_ans, hv, hv, dev_u, NULL);
+            softmax_in(&sf_out, V, hv, hv, ds_ans.dev_out_vec, NULL);
+            cross_entropy_in(&ce, hv, hv, sf_out.dev_out_vec, dev_a + (size_t)i * V);
 
             /* forward: MemN2N.c:2626-2697 */
             dense_fwd(&emb_q, false);

@@ -126,14 +126,18 @@ class Stories:
 
 
 def make_stories(cfg: ModelConfig, N: int, seed: int, S: Optional[int] = None, ragged: bool = False,
-                 min_words: int = 2, max_words: int = 6, q_words: int = 3) -> Stories:
+                 min_words: int = 2, max_words: int = 6, q_words: int = 3,
+                 n_sen: Optional[np.ndarray] = None) -> Stories:
     """bAbI-shaped stories: each sentence is a bag of 2..6 word ids uniform in [1, V_dict) plus the
     one-hot time column V_dict + n_sen-1-j (MemN2N/sample.c:466-476, 544-548); words are drawn
     with replacement, so counts of 2 occur (SURVEY hard part 5)."""
     rng = np.random.default_rng(seed)
     S = cfg.S_max if S is None else S
     assert S <= cfg.S_max and cfg.V_dict >= 2 and cfg.V_dict + cfg.S_max <= cfg.V
-    n_sen = (rng.integers(1, S + 1, size=N) if ragged else np.full(N, S)).astype(np.uint32)
+    if n_sen is None:
+        n_sen = rng.integers(1, S + 1, size=N) if ragged else np.full(N, S)
+    n_sen = np.asarray(n_sen).astype(np.uint32)
+    assert n_sen.shape == (N,) and int(n_sen.max(initial=0)) <= cfg.S_max
     tot = int(n_sen.sum())
     m = np.zeros((tot, cfg.V), dtype=np.float32)
     nw = rng.integers(min_words, max_words + 1, size=tot)
