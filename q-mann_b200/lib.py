@@ -1,0 +1,215 @@
+"""ctypes binding of libqmann_b200.so (C ABI: include/qmann_abi.h).
+
+torch is used only as the owner of device memory and streams: every call below passes raw
+device pointers (tensor.data_ptr()) into the C ABI.  There is no CPU fallback: if the CUDA library
+is not built this module raises at load time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqmann_b200.so")
+MAX_HOP = 8
+
+_FP = C.c_void_p
+_U32 = C.c_uint32
+
+
+class QConfig(C.Structure):
+    _fields_ = [("V", _U32), ("d", _U32), ("S_max", _U32), ("H", _U32), ("mode", _U32), ("lin_map", _U32),
+                ("const_scale", C.c_int32),
+                ("iwl", _U32 * MAX_HOP), ("frac", _U32 * MAX_HOP), ("iwl_w", _U32 * MAX_HOP), ("frac_w", _U32 * MAX_HOP),
+                ("iwl_att", _U32 * MAX_HOP), ("frac_att", _U32 * MAX_HOP), ("iwl_bin", _U32), ("frac_bin", _U32)]
+
+
+class QWeights(C.Structure):
+    _fields_ = [("dev_B", _FP), ("dev_A", _FP * MAX_HOP), ("dev_C", _FP * MAX_HOP), ("dev_Hm", _FP * MAX_HOP), ("dev_W", _FP)]
+
+
+class QDebug(C.Structure):
+    _fields_ = [(f"dev_{k}", _FP) for k in ("u0", "M", "C", "s", "p", "o", "g", "u", "z", "h")]
+
+
+def build(force: bool = False, extra: str = "") -> str:
+    """Compile libqmann_b200.so for sm_100a with the committed recipe (csrc/Makefile)."""
+    srcdir = os.path.join(_HERE, "csrc")
+    if force and os.path.exists(LIB_PATH):
+        os.remove(LIB_PATH)
+    cmd = ["make", "-C", srcdir]
+    if extra:
+        cmd.append(f"EXTRA={extra}")
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library.  Raises (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc -gencode arch=compute_100a,code=sm_100a); qmann_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.qmann_last_error.restype = C.c_char_p
+    L.qmann_version.restype = C.c_char_p
+    L.qmann_launch_count.restype = C.c_uint64
+    L.qmann_model_create.restype = C.c_int
+    L.qmann_model_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(QConfig), C.POINTER(QWeights)]
+    L.qmann_model_destroy.restype = None
+    L.qmann_model_destroy.argtypes = [C.c_void_p]
+    L.qmann_batch_create.restype = C.c_int
+    L.qmann_batch_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_U32), _U32]
+    L.qmann_batch_destroy.restype = None
+    L.qmann_batch_destroy.argtypes = [C.c_void_p]
+    L.qmann_forward_batch.restype = C.c_int
+    L.qmann_forward_batch.argtypes = [C.c_void_p, C.c_void_p, _FP, _FP, _FP, _FP, _FP, _FP, C.POINTER(QDebug), C.c_void_p]
+    L.qmann_infer_host.restype = C.c_int
+    L.qmann_infer_host.argtypes = [C.c_void_p, _FP, _FP, _FP, C.POINTER(_U32), _U32, C.POINTER(_U32), C.POINTER(_U32),
+                                   C.POINTER(C.c_float)]
+    L.qmann_shard_plan.restype = C.c_int
+    L.qmann_shard_plan.argtypes = [C.POINTER(_U32), _U32, _U32, _U32, C.POINTER(_U32), C.POINTER(_U32)]
+    _lib = L
+    return L
+
+
+class QmannError(RuntimeError):
+    pass
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise QmannError(f"qmann error {rc}: {lib().qmann_last_error().decode()}")
+
+
+def make_config(cfg) -> QConfig:
+    f = cfg.formats()
+    q = QConfig()
+    q.V, q.d, q.S_max, q.H, q.mode, q.lin_map, q.const_scale = cfg.V, cfg.d, cfg.S_max, cfg.H, cfg.mode, int(cfg.lin_map), cfg.const_scale
+    for h in range(cfg.H):
+        q.iwl[h], q.frac[h] = f["iwl"][h], f["frac"][h]
+        q.iwl_w[h], q.frac_w[h] = f["iwl_w"][h], f["frac_w"][h]
+        q.iwl_att[h], q.frac_att[h] = f["iwl_att"][h], f["frac_att"][h]
+    q.iwl_bin, q.frac_bin = f["iwl_bin"], f["frac_bin"]
+    return q
+
+
+def shard_plan(n_sen: np.ndarray, world: int, rank: int):
+    """Contiguous story range of `rank` (qmann_shard_plan); pure host arithmetic."""
+    ns = np.ascontiguousarray(n_sen, dtype=np.uint32)
+    first, count = _U32(0), _U32(0)
+    _check(lib().qmann_shard_plan(ns.ctypes.data_as(C.POINTER(_U32)), len(ns), world, rank, C.byref(first), C.byref(count)))
+    return int(first.value), int(count.value)
+
+
+class Model:
+    """Quantised model resident on the current CUDA device (mirror of the layer structs the reference
+    driver builds at MemN2N/MemN2N.c:826-912, collapsed into one object)."""
+
+    def __init__(self, cfg, weights, device: str = "cuda:0"):
+        import torch
+        self.torch = torch
+        self.cfg = cfg
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
+        self.w = dict(B=t(weights.B), W=t(weights.W), A=[t(x) for x in weights.A], C=[t(x) for x in weights.C],
+                      Hm=[t(x) for x in weights.Hm])
+        qw = QWeights()
+        qw.dev_B, qw.dev_W = self.w["B"].data_ptr(), self.w["W"].data_ptr()
+        for h in range(cfg.H):
+            qw.dev_A[h], qw.dev_C[h], qw.dev_Hm[h] = self.w["A"][h].data_ptr(), self.w["C"][h].data_ptr(), self.w["Hm"][h].data_ptr()
+        self._h = C.c_void_p()
+        qc = make_config(cfg)
+        _check(lib().qmann_model_create(C.byref(self._h), C.byref(qc), C.byref(qw)))
+
+    def close(self):
+        if self._h:
+            lib().qmann_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device-resident batch ---------------------------------------------------------------
+    def upload(self, st) -> "DeviceBatch":
+        return DeviceBatch(self, st)
+
+    def forward(self, db: "DeviceBatch", with_answers: bool = True, want_h: bool = False, debug: bool = False,
+                stream=None) -> Dict[str, object]:
+        """One pass of the hot path over the whole device-resident batch (asynchronous)."""
+        torch = self.torch
+        N, H, d, V, ss = db.N, self.cfg.H, self.cfg.d, self.cfg.V, db.sum_sen
+        out: Dict[str, object] = {}
+        out["pred"] = db.pred
+        db.match.zero_()
+        dbg = None
+        if debug:
+            dbg = QDebug()
+            shapes = dict(u0=(N, d), M=(H, ss, d), C=(H, ss, d), s=(H, ss), p=(H, ss), o=(H, N, d), g=(H, N, d), u=(H, N, d),
+                          z=(N, V), h=(N, V))
+            for k, shp in shapes.items():
+                out[k] = torch.zeros(shp, dtype=torch.float32, device=self.device)
+                setattr(dbg, f"dev_{k}", out[k].data_ptr())
+        sptr = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        _check(lib().qmann_forward_batch(self._h, db._h, db.m.data_ptr(), db.q.data_ptr(),
+                                         db.a.data_ptr() if with_answers else None, db.pred.data_ptr(),
+                                         db.h_true.data_ptr() if want_h else None,
+                                         db.match.data_ptr() if with_answers else None,
+                                         C.byref(dbg) if dbg is not None else None, C.c_void_p(sptr)))
+        out["match"] = db.match
+        out["h_true"] = db.h_true
+        return out
+
+    # ---- host arenas in, predictions out (the call a user of the reference would make) -------
+    def infer_host(self, m: np.ndarray, q: np.ndarray, a: Optional[np.ndarray], n_sen: np.ndarray, want_cost: bool = False):
+        N = len(n_sen)
+        pred = np.zeros(N, dtype=np.uint32)
+        match, cost = _U32(0), C.c_float(0.0)
+        ns = np.ascontiguousarray(n_sen, dtype=np.uint32)
+        ptr = lambda x: None if x is None else C.c_void_p(x.ctypes.data if isinstance(x, np.ndarray) else x.data_ptr())
+        _check(lib().qmann_infer_host(self._h, ptr(m), ptr(q), ptr(a), ns.ctypes.data_as(C.POINTER(_U32)), N,
+                                      pred.ctypes.data_as(C.POINTER(_U32)), C.byref(match),
+                                      C.byref(cost) if want_cost else None))
+        return pred, int(match.value), float(cost.value)
+
+
+class DeviceBatch:
+    """Packed stories resident in HBM: the arenas cuda_data_in() fills (MemN2N.c:2336-2350)."""
+
+    def __init__(self, model: Model, st):
+        torch = model.torch
+        dev = model.device
+        self.N, self.sum_sen = st.N, st.sum_sen
+        self.m = torch.from_numpy(np.ascontiguousarray(st.m, dtype=np.float32)).to(dev)
+        self.q = torch.from_numpy(np.ascontiguousarray(st.q, dtype=np.float32)).to(dev)
+        self.a = torch.from_numpy(np.ascontiguousarray(st.a, dtype=np.float32)).to(dev)
+        self.pred = torch.zeros(max(1, st.N), dtype=torch.int32, device=dev)
+        self.h_true = torch.zeros(max(1, st.N), dtype=torch.float32, device=dev)
+        self.match = torch.zeros(1, dtype=torch.int32, device=dev)
+        ns = np.ascontiguousarray(st.n_sen, dtype=np.uint32)
+        self._h = C.c_void_p()
+        _check(lib().qmann_batch_create(C.byref(self._h), ns.ctypes.data_as(C.POINTER(_U32)), st.N))
+
+    def close(self):
+        if self._h:
+            lib().qmann_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
