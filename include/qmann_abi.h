@@ -213,6 +213,13 @@ int  qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, 
 int  qmann_shard_plan(const uint32_t *n_sen, uint32_t N, uint32_t world, uint32_t rank,
                       uint32_t *first, uint32_t *count);
 
+/* Optional per-kernel timing: while enabled, qmann_forward_batch/qmann_infer_host bracket each of
+ * their two kernels with CUDA events on the launching stream.  qmann_profile_read() synchronises
+ * on them, returns the summed durations (ms) and the number of (compact, forward) launch pairs,
+ * and resets the accumulation. */
+int  qmann_profile_enable(qmann_model *m, int enable);
+int  qmann_profile_read(qmann_model *m, float *ms_compact, float *ms_forward, uint32_t *n_pairs);
+
 /* Number of kernel launches issued by this library since load (for benchmarks' accounting). */
 uint64_t qmann_launch_count(void);
 const char *qmann_last_error(void);

@@ -775,6 +775,16 @@ struct qmann_model {
     unsigned long long heap_cap;
     unsigned long long *dev_heap_used;
     unsigned *dev_counter, *dev_err;
+    // qmann_infer_host staging (grow-only device arenas, two streams)
+    float *e2e_m = nullptr, *e2e_q = nullptr, *e2e_a = nullptr, *e2e_h = nullptr;
+    uint32_t *e2e_pred = nullptr, *e2e_match = nullptr;
+    size_t e2e_m_cap = 0, e2e_n_cap = 0;
+    cudaStream_t e2e_compute = nullptr, e2e_copy = nullptr;
+    std::vector<cudaEvent_t> e2e_events;
+    // optional per-kernel timing (qmann_profile_*)
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;     // triples: before compact, between, after forward
+    size_t prof_used = 0;
 };
 
 struct qmann_batch {
@@ -976,6 +986,11 @@ void qmann_model_destroy(qmann_model *m)
     if (!m) return;
     cudaFree(m->dev_img); cudaFree(m->dev_rec); cudaFree(m->dev_heap); cudaFree(m->dev_heap_used);
     cudaFree(m->dev_counter); cudaFree(m->dev_err);
+    cudaFree(m->e2e_m); cudaFree(m->e2e_q); cudaFree(m->e2e_a); cudaFree(m->e2e_h); cudaFree(m->e2e_pred); cudaFree(m->e2e_match);
+    if (m->e2e_compute) cudaStreamDestroy(m->e2e_compute);
+    if (m->e2e_copy) cudaStreamDestroy(m->e2e_copy);
+    for (auto e : m->e2e_events) cudaEventDestroy(e);
+    for (auto e : m->prof_events) cudaEventDestroy(e);
     delete m;
 }
 
@@ -1023,10 +1038,20 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
         QCUDA(cudaMemsetAsync(m->dev_heap_used, 0, sizeof(unsigned long long), st));
         QCUDA(cudaMemsetAsync(m->dev_counter, 0, sizeof(unsigned), st));
         const unsigned cblocks = std::min<unsigned>((n + 7) / 8, (unsigned)m->sm_count * 8);
+        cudaEvent_t *pe = nullptr;
+        if (m->profile) {
+            if (m->prof_used + 3 > m->prof_events.size()) {
+                for (int k = 0; k < 3; k++) { cudaEvent_t e; QCUDA(cudaEventCreate(&e)); m->prof_events.push_back(e); }
+            }
+            pe = &m->prof_events[m->prof_used];
+            m->prof_used += 3;
+            QCUDA(cudaEventRecord(pe[0], st));
+        }
         if (vec4) k_compact<true><<<cblocks, 256, 0, st>>>(cp);
         else      k_compact<false><<<cblocks, 256, 0, st>>>(cp);
         count_launch();
         QCUDA(cudaPeekAtLastError());
+        if (pe) QCUDA(cudaEventRecord(pe[1], st));
 
         FwdParams p = m->base;
         p.sen_off = b->dev_sen_off; p.story0 = s0; p.n_stories = n; p.n_total = b->N; p.sum_sen = b->sum_sen;
@@ -1034,6 +1059,7 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
         if (dbg) p.dbg = *dbg;
         int rc = launch_forward(m, p, debug, st);
         if (rc) return rc;
+        if (pe) QCUDA(cudaEventRecord(pe[2], st));
     }
     return QMANN_OK;
 }
@@ -1075,53 +1101,61 @@ int qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, c
     qmann_batch *b = nullptr;
     int rc = qmann_batch_create(&b, n_sen, N);
     if (rc) return rc;
+    if (b->max_sen > m->cfg.S_max) { qmann_batch_destroy(b); return fail(QMANN_E_ARG, "a story has more sentences than S_max"); }
     const size_t V = m->cfg.V;
-    float *dm = nullptr, *dq = nullptr, *da = nullptr, *dh = nullptr;
-    uint32_t *dp = nullptr, *dmatch = nullptr;
-    cudaStream_t sc = nullptr, sx = nullptr;
-    std::vector<cudaEvent_t> evs;
-    auto cleanup = [&]() {
-        cudaFree(dm); cudaFree(dq); cudaFree(da); cudaFree(dh); cudaFree(dp); cudaFree(dmatch);
-        if (sc) cudaStreamDestroy(sc);
-        if (sx) cudaStreamDestroy(sx);
-        for (auto e : evs) cudaEventDestroy(e);
-        qmann_batch_destroy(b);
-    };
-#define QC2(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(QMANN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
-    QC2(cudaMalloc((void **)&dm, std::max<size_t>(1, b->sum_sen * V) * sizeof(float)));
-    QC2(cudaMalloc((void **)&dq, std::max<size_t>(1, (size_t)N * V) * sizeof(float)));
-    if (a_host) QC2(cudaMalloc((void **)&da, std::max<size_t>(1, (size_t)N * V) * sizeof(float)));
-    if (a_host && cost) QC2(cudaMalloc((void **)&dh, std::max<size_t>(1, (size_t)N) * sizeof(float)));
-    QC2(cudaMalloc((void **)&dp, std::max<size_t>(1, (size_t)N) * sizeof(uint32_t)));
-    QC2(cudaMalloc((void **)&dmatch, sizeof(uint32_t)));
-    QC2(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-    QC2(cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking));
-    QC2(cudaMemsetAsync(dmatch, 0, sizeof(uint32_t), sc));
-    // copy stream runs ahead in chunks; the compute stream waits per chunk, so the H2D of chunk
-    // k+1 overlaps the kernels of chunk k
-    const uint32_t CH = 8192;
+#define QC2(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { qmann_batch_destroy(b); return fail(QMANN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    // grow-only device arenas owned by the model: repeated calls reuse them
+    if (b->sum_sen > m->e2e_m_cap) {
+        cudaFree(m->e2e_m); m->e2e_m = nullptr; m->e2e_m_cap = 0;
+        QC2(cudaMalloc((void **)&m->e2e_m, std::max<size_t>(1, b->sum_sen * V) * sizeof(float)));
+        m->e2e_m_cap = b->sum_sen;
+    }
+    if (N > m->e2e_n_cap) {
+        cudaFree(m->e2e_q); cudaFree(m->e2e_a); cudaFree(m->e2e_h); cudaFree(m->e2e_pred);
+        m->e2e_q = m->e2e_a = m->e2e_h = nullptr; m->e2e_pred = nullptr; m->e2e_n_cap = 0;
+        QC2(cudaMalloc((void **)&m->e2e_q, (size_t)N * V * sizeof(float)));
+        QC2(cudaMalloc((void **)&m->e2e_a, (size_t)N * V * sizeof(float)));
+        QC2(cudaMalloc((void **)&m->e2e_h, (size_t)N * sizeof(float)));
+        QC2(cudaMalloc((void **)&m->e2e_pred, (size_t)N * sizeof(uint32_t)));
+        m->e2e_n_cap = N;
+    }
+    if (!m->e2e_match) QC2(cudaMalloc((void **)&m->e2e_match, sizeof(uint32_t)));
+    if (!m->e2e_compute) QC2(cudaStreamCreateWithFlags(&m->e2e_compute, cudaStreamNonBlocking));
+    if (!m->e2e_copy) QC2(cudaStreamCreateWithFlags(&m->e2e_copy, cudaStreamNonBlocking));
+    cudaStream_t sc = m->e2e_compute, sx = m->e2e_copy;
+    float *dm = m->e2e_m, *dq = m->e2e_q, *da = a_host ? m->e2e_a : nullptr, *dh = (a_host && cost) ? m->e2e_h : nullptr;
+    QC2(cudaMemsetAsync(m->e2e_match, 0, sizeof(uint32_t), sc));
+    // the copy stream runs ahead chunk by chunk; the compute stream waits per chunk, so the H2D of
+    // chunk k+1 overlaps the kernels of chunk k
+    const uint32_t CH = 4096;
+    size_t ev_i = 0;
     for (uint32_t s0 = 0; s0 < N; s0 += CH) {
         const uint32_t n = std::min<uint32_t>(CH, N - s0);
         const size_t r0 = b->sen_off[s0], r1 = b->sen_off[s0 + n];
         if (r1 > r0) QC2(cudaMemcpyAsync(dm + r0 * V, m_host + r0 * V, (r1 - r0) * V * sizeof(float), cudaMemcpyHostToDevice, sx));
         QC2(cudaMemcpyAsync(dq + (size_t)s0 * V, q_host + (size_t)s0 * V, (size_t)n * V * sizeof(float), cudaMemcpyHostToDevice, sx));
-        if (a_host) QC2(cudaMemcpyAsync(da + (size_t)s0 * V, a_host + (size_t)s0 * V, (size_t)n * V * sizeof(float), cudaMemcpyHostToDevice, sx));
-        cudaEvent_t ev;
-        QC2(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        evs.push_back(ev);
+        if (da) QC2(cudaMemcpyAsync(da + (size_t)s0 * V, a_host + (size_t)s0 * V, (size_t)n * V * sizeof(float), cudaMemcpyHostToDevice, sx));
+        if (ev_i >= m->e2e_events.size()) {
+            cudaEvent_t ev;
+            QC2(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            m->e2e_events.push_back(ev);
+        }
+        cudaEvent_t ev = m->e2e_events[ev_i++];
         QC2(cudaEventRecord(ev, sx));
         QC2(cudaStreamWaitEvent(sc, ev, 0));
-        rc = forward_range(m, b, s0, n, dm, dq, da, dp, dh, a_host ? dmatch : nullptr, nullptr, sc);
-        if (rc) { cleanup(); return rc; }
+        rc = forward_range(m, b, s0, n, dm, dq, da, m->e2e_pred, dh, da ? m->e2e_match : nullptr, nullptr, sc);
+        if (rc) { qmann_batch_destroy(b); return rc; }
     }
-    QC2(cudaMemcpyAsync(pred_host, dp, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+    QC2(cudaMemcpyAsync(pred_host, m->e2e_pred, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
     uint32_t mt = 0;
-    QC2(cudaMemcpyAsync(&mt, dmatch, sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+    QC2(cudaMemcpyAsync(&mt, m->e2e_match, sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
     std::vector<float> ht;
     if (dh) { ht.resize(N); QC2(cudaMemcpyAsync(ht.data(), dh, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, sc)); }
     unsigned err = 0;
     QC2(cudaMemcpyAsync(&err, m->dev_err, sizeof(unsigned), cudaMemcpyDeviceToHost, sc));
     QC2(cudaStreamSynchronize(sc));
+#undef QC2
+    qmann_batch_destroy(b);
     if (match) *match = mt;
     if (cost && dh) {
         // the reference accumulates cost += -h[y] story by story in fp32 (layer_cuda.cu:2198)
@@ -1129,9 +1163,33 @@ int qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, c
         for (uint32_t i = 0; i < N; i++) cacc = (float)((double)cacc + -1.0 * (double)ht[i]);
         *cost = cacc;
     }
-    cleanup();
-#undef QC2
     if (err) return fail(QMANN_E_NOMEM, "a story overflowed the compaction heap");
+    return QMANN_OK;
+}
+
+int qmann_profile_enable(qmann_model *m, int enable)
+{
+    if (!m) return fail(QMANN_E_ARG, "null model");
+    m->profile = enable != 0;
+    m->prof_used = 0;
+    return QMANN_OK;
+}
+
+int qmann_profile_read(qmann_model *m, float *ms_compact, float *ms_forward, uint32_t *n_pairs)
+{
+    if (!m) return fail(QMANN_E_ARG, "null model");
+    double tc = 0.0, tf = 0.0;
+    for (size_t i = 0; i + 3 <= m->prof_used; i += 3) {
+        float a = 0.f, b2 = 0.f;
+        QCUDA(cudaEventSynchronize(m->prof_events[i + 2]));
+        QCUDA(cudaEventElapsedTime(&a, m->prof_events[i], m->prof_events[i + 1]));
+        QCUDA(cudaEventElapsedTime(&b2, m->prof_events[i + 1], m->prof_events[i + 2]));
+        tc += a; tf += b2;
+    }
+    if (ms_compact) *ms_compact = (float)tc;
+    if (ms_forward) *ms_forward = (float)tf;
+    if (n_pairs) *n_pairs = (uint32_t)(m->prof_used / 3);
+    m->prof_used = 0;
     return QMANN_OK;
 }
 

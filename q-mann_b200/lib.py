@@ -76,6 +76,10 @@ def lib() -> C.CDLL:
     L.qmann_infer_host.restype = C.c_int
     L.qmann_infer_host.argtypes = [C.c_void_p, _FP, _FP, _FP, C.POINTER(_U32), _U32, C.POINTER(_U32), C.POINTER(_U32),
                                    C.POINTER(C.c_float)]
+    L.qmann_profile_enable.restype = C.c_int
+    L.qmann_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.qmann_profile_read.restype = C.c_int
+    L.qmann_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_U32)]
     L.qmann_shard_plan.restype = C.c_int
     L.qmann_shard_plan.argtypes = [C.POINTER(_U32), _U32, _U32, _U32, C.POINTER(_U32), C.POINTER(_U32)]
     _lib = L
@@ -142,6 +146,15 @@ class Model:
             self.close()
         except Exception:
             pass
+
+    def profile(self, enable: bool):
+        _check(lib().qmann_profile_enable(self._h, int(enable)))
+
+    def profile_read(self):
+        """(ms in k_compact, ms in k_forward, launch pairs) since the last read; synchronises."""
+        a, b, n = C.c_float(0), C.c_float(0), _U32(0)
+        _check(lib().qmann_profile_read(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return float(a.value), float(b.value), int(n.value)
 
     # ---- device-resident batch ---------------------------------------------------------------
     def upload(self, st) -> "DeviceBatch":
