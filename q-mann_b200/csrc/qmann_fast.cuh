@@ -1,0 +1,402 @@
+// qmann_fast.cuh -- the production forward kernel (included by qmann_forward.cu after
+// qmann_kernels.cuh).
+//
+// k_forward_fast handles the stories k_compact classified as regular: every bag-of-words value is
+// 1.0 after count splitting (no exception entries), the unit-entry list fits a warp's shared-memory
+// slot, and every weight format has at least one integer bit (Q_w(1.0) = 2^frac_w).  Any other story
+// is appended to p.slow_list and processed afterwards by the general kernel k_forward (same
+// arithmetic, every input accepted) -- a second CUDA launch, not a CPU fallback.
+//
+// The code is kept small on purpose (the general kernel is ~130 KB of SASS and thrashes the
+// instruction cache when 16 warps sit in different phases): no debug outputs, no rare paths,
+// bounded unrolling.
+#pragma once
+#include "qmann_kernels.cuh"
+
+namespace {
+
+// acc[j] = sum over the unit entries of `row` of the int8 table codes of dims 16q..16q+15.
+// Lanes past their row's end gather the all-zero row V through the pseudo entry at `zaddr`.
+template <int LPR>
+__device__ __forceinline__ void embed_fast(const FwdParams &p, unsigned ws, unsigned lane, unsigned tab, int row, int acc[16], const int sel[4])
+{
+    const unsigned q = lane % LPR;
+#pragma unroll
+    for (int j = 0; j < 16; j++) acc[j] = 0;
+    unsigned beg = 0, len = 0;
+    if (row >= 0) {
+        const unsigned short *rend = reinterpret_cast<const unsigned short *>(smem + ws + p.o_rend);
+        beg = row ? rend[row - 1] : 0u;
+        len = rend[row] - beg;
+    }
+    const unsigned maxlen = __reduce_max_sync(0xffffffffu, len);
+    const unsigned tabq = tab + 16u * q;
+    unsigned ea = ws + 4u * beg;
+    const unsigned zaddr = ws + p.o_zent;
+#pragma unroll 4
+    for (unsigned k = 0; k < maxlen; k++, ea += 4u) {
+        const unsigned col = *reinterpret_cast<const unsigned *>(smem + ((k < len) ? ea : zaddr));
+        const uint4 t = *reinterpret_cast<const uint4 *>(smem + tabq + col * p.DP);
+        acc[0] = __dp4a((int)t.x, sel[0], acc[0]);   acc[1] = __dp4a((int)t.x, sel[1], acc[1]);
+        acc[2] = __dp4a((int)t.x, sel[2], acc[2]);   acc[3] = __dp4a((int)t.x, sel[3], acc[3]);
+        acc[4] = __dp4a((int)t.y, sel[0], acc[4]);   acc[5] = __dp4a((int)t.y, sel[1], acc[5]);
+        acc[6] = __dp4a((int)t.y, sel[2], acc[6]);   acc[7] = __dp4a((int)t.y, sel[3], acc[7]);
+        acc[8] = __dp4a((int)t.z, sel[0], acc[8]);   acc[9] = __dp4a((int)t.z, sel[1], acc[9]);
+        acc[10] = __dp4a((int)t.z, sel[2], acc[10]); acc[11] = __dp4a((int)t.z, sel[3], acc[11]);
+        acc[12] = __dp4a((int)t.w, sel[0], acc[12]); acc[13] = __dp4a((int)t.w, sel[1], acc[13]);
+        acc[14] = __dp4a((int)t.w, sel[2], acc[14]); acc[15] = __dp4a((int)t.w, sel[3], acc[15]);
+    }
+}
+
+// One lane's share (16 dims) of  sum_t ( Q_att( Q_att(M[r][t]) * Q_bin(u[t]) ) + la ):
+// y = clamp(m) + L in one VIADDMNMX.RELU, x = y*u - L*u in one IMAD (cub = -L*u), truncating shift
+// in three ops, clamp + la in one more, accumulate.                        layer_cuda.cu:105-141
+// KA = sign of (frac_att - frac_w), the re-quantisation of M from the weight to the addressing format:
+//   KA == 0: same grid, one clamp (la == lw)
+//   KA  > 0: clamp_att(clamp_w(a) << k) == clamp_att(a << k) because la <= lw << k
+//   KA  < 0: trunc0(clamp_w(a) / 2^k) == clamp(trunc0(a / 2^k), lw >> k) (both maps are odd and monotone)
+template <int KA>
+__device__ __forceinline__ int score_fast(const int acc[16], const int ub[16], const int cub[16], int L, int ksh, int la, int fb, int mb)
+{
+    const int L2 = 2 * L, la2 = 2 * la, mk = (1 << ksh) - 1;
+    int part = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        int a = acc[j];
+        if (KA > 0) a <<= ksh;
+        if (KA < 0) a = shr0m(a, ksh, mk);
+        const int y = clamp_biased(a, L, L2);
+        const int x = y * ub[j] + cub[j];
+        part += clamp_biased(shr0m(x, fb, mb), la, la2);
+    }
+    return part;
+}
+
+template <int LPR, int MODE>
+__global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__ FwdParams p)
+{
+    constexpr int G = 32 / LPR;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned g = lane / LPR, q = lane % LPR;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.img);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (unsigned i = threadIdx.x; i < p.img_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const unsigned wso = p.tables_bytes + wid * p.warp_bytes;
+    unsigned char *ws = smem + wso;
+    unsigned *ent_s = reinterpret_cast<unsigned *>(ws);
+    unsigned short *rend_s = reinterpret_cast<unsigned short *>(ws + p.o_rend);
+    int *sc = reinterpret_cast<int *>(ws + p.o_sc);
+    float *ex = reinterpret_cast<float *>(ws + p.o_ex);
+    unsigned char *pq = ws + p.o_pq;
+    signed char *uvec = reinterpret_cast<signed char *>(ws + p.o_uvec);
+    int *ub32 = reinterpret_cast<int *>(ws + p.o_ub32);
+    signed char *ovec = reinterpret_cast<signed char *>(ws + p.o_ovec);
+    float *ufl = reinterpret_cast<float *>(ws + p.o_ufl);
+    float *zbuf = reinterpret_cast<float *>(ws);      // aliases the entry list (dead by the answer phase)
+    if (lane == 0) *reinterpret_cast<unsigned *>(ws + p.o_zent) = p.V;
+    const unsigned d = p.d, DP = p.DP, V = p.V;
+    int sel[4];
+    asm volatile("mov.u32 %0, 0x00000001;" : "=r"(sel[0]));
+    asm volatile("mov.u32 %0, 0x00000100;" : "=r"(sel[1]));
+    asm volatile("mov.u32 %0, 0x00010000;" : "=r"(sel[2]));
+    asm volatile("mov.u32 %0, 0x01000000;" : "=r"(sel[3]));
+
+#pragma unroll 1
+    for (;;) {
+        unsigned w = 0;
+        if (lane == 0) w = atomicAdd(p.counter, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= p.n_stories) break;
+        const unsigned story = p.story0 + w;
+        const unsigned S = (unsigned)(p.sen_off[story + 1] - p.sen_off[story]);
+
+        const unsigned char *rec = p.rec + (size_t)w * p.rec_stride;
+        const unsigned *hdr = reinterpret_cast<const unsigned *>(rec);
+        const unsigned n_ent = hdr[0], flags = hdr[1], ans_idx = hdr[2], n_exc = hdr[4];
+        if (flags != 0u || n_exc != 0u || n_ent > p.LW) {
+            // not a regular story: leave it to the general kernel
+            if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = w;
+            continue;
+        }
+        {
+            const unsigned short *rend_g = reinterpret_cast<const unsigned short *>(rec + p.off_rend);
+            for (unsigned r = lane; r < S + 1; r += 32) rend_s[r] = rend_g[r];
+            const unsigned *ent_g = reinterpret_cast<const unsigned *>(rec + p.off_ent);
+            for (unsigned k = lane; k < n_ent; k += 32) ent_s[k] = ent_g[k];
+        }
+        __syncwarp();
+
+        int acc[16];
+        // ---- question embedding u0 = Q_w0(sum)                                 MemN2N.c:826, layer_cuda.cu:49 ----
+        embed_fast<LPR>(p, wso, lane, p.offB, (g == 0) ? 0 : -1, acc, sel);
+        if (g == 0) {
+            unsigned packed[4];
+#pragma unroll
+            for (int w4 = 0; w4 < 4; w4++) {
+                unsigned v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) v |= ((unsigned)(qi_clamp(acc[4 * w4 + b], p.lw[0]) & 0xFF)) << (8 * b);
+                packed[w4] = v;
+            }
+            *reinterpret_cast<uint4 *>(uvec + 16 * q) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        __syncwarp();
+        int fu = p.fw[0];
+
+#pragma unroll 1
+        for (unsigned h = 0; h < p.H; h++) {
+            const int fw = p.fw[h], lw = p.lw[h];
+            const int fa = p.fa[h], la = p.la[h];
+            const int ff = p.ff[h], lf = p.lf[h];
+            const int fb = p.fb, lb = p.lb;
+            const int mb = (1 << fb) - 1;
+
+            // u operand Q_bin(u) as int32                                        MemN2N.c:847,873
+            for (unsigned j = lane; j < DP; j += 32) ub32[j] = (j < d) ? qi_requant((int)uvec[j], fu, lb, fb) : 0;
+            __syncwarp();
+            const int ka = fa - fw;
+            // scorer constants: clamp limit of the re-quantised memory value and -L*u per dim
+            const int Ls = (ka < 0) ? min(la, lw >> (-ka)) : la;
+            const bool simple = (ka == 0) ? (la == lw) : (ka > 0 ? (la <= (lw << ka)) : true);
+            int ub[16], cub[16];
+            unsigned au[16];
+            unsigned su_bits = 0;
+            if (MODE == 3) {
+                const uint4 t = *reinterpret_cast<const uint4 *>(uvec + 16 * q);
+                const unsigned tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    unsigned s_, m_;
+                    appx_encode(sbyte(tw[j >> 2], j & 3), fu, p.ia[h], s_, m_);     // layer.c:215-233, layer_cuda.cu:2515
+                    au[j] = m_;
+                    su_bits |= (s_ >> 31) << j;
+                }
+            } else {
+#pragma unroll
+                for (int w4 = 0; w4 < 4; w4++) {
+                    const int4 t = *reinterpret_cast<const int4 *>(ub32 + 16 * q + 4 * w4);
+                    ub[4 * w4 + 0] = t.x; ub[4 * w4 + 1] = t.y; ub[4 * w4 + 2] = t.z; ub[4 * w4 + 3] = t.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j++) cub[j] = -Ls * ub[j];
+            }
+
+            // ---- memory embedding + addressing, G rows per pass ----
+#pragma unroll 1
+            for (unsigned r0 = 0; r0 < S; r0 += G) {
+                const unsigned r = r0 + g;
+                embed_fast<LPR>(p, wso, lane, p.offA[h], (r < S) ? (int)(r + 1) : -1, acc, sel);
+                int part = 0;
+                if (MODE == 3) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        unsigned sm, am;
+                        appx_encode(qi_clamp(acc[j], lw), fw, p.ia[h], sm, am);
+                        const unsigned sv = ((su_bits >> j) & 1u) << 31;
+                        part += (16u * q + j < d) ? appx_element_x128(sm, am, sv, au[j]) : 0;
+                    }
+                } else if (!simple) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) part += qi_mul(qi_requant(qi_clamp(acc[j], lw), fw, la, fa), ub[j], la, fb);
+                } else {
+                    if (ka == 0) part = score_fast<0>(acc, ub, cub, Ls, 0, la, fb, mb);
+                    else if (ka > 0) part = score_fast<1>(acc, ub, cub, Ls, ka, la, fb, mb);
+                    else part = score_fast<-1>(acc, ub, cub, Ls, -ka, la, fb, mb);
+                    part -= 16 * la;
+                }
+                const int tot = group_sum<LPR>(part);
+                if (q == 0 && r < S) sc[r] = (MODE == 3) ? tot : qi_clamp(tot, la);
+            }
+            __syncwarp();
+
+            // ---- attention normalisation (layer_cuda.cu:1895-1916, 1969-2060) ----
+            float mx = -INFINITY;
+            for (unsigned r = lane; r < S; r += 32) {
+                float sv;
+                if (MODE == 3) {
+                    const int sh = 7 - p.const_scale;
+                    const float v = (float)sc[r] / (float)(1 << sh);
+                    const float lim = (float)(1 << p.ia[h]);
+                    sv = (v >= lim) ? lim : (v < -lim ? -lim : (v == -lim ? 0.0f : v));
+                } else {
+                    sv = (float)sc[r] / (float)(1 << fa);
+                }
+                ex[r] = sv;
+                mx = fmaxf(mx, sv);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            for (unsigned r = lane; r < S; r += 32) ex[r] = __expf(ex[r] - mx);
+            __syncwarp();
+            double total = 0.0;
+#pragma unroll 2
+            for (unsigned r = 0; r < S; r++) total += (double)ex[r];
+            unsigned nnz = 0;
+#pragma unroll 1
+            for (unsigned r0 = 0; r0 < S; r0 += 32) {
+                const unsigned r = r0 + lane;
+                unsigned code = 0;
+                if (r < S) code = (unsigned)qi_encode((float)((double)ex[r] / total), p.iff[h], ff);      // layer_cuda.cu:561
+                const unsigned b = __ballot_sync(0xffffffffu, code != 0u);
+                if (code) {
+                    const unsigned k = nnz + __popc(b & ((1u << lane) - 1u));
+                    sc[k] = (int)r;
+                    pq[k] = (unsigned char)code;
+                }
+                nnz += __popc(b);
+            }
+            __syncwarp();
+
+            // ---- weighted read over the slots with a non-zero quantised weight (layer_cuda.cu:547-579) ----
+            int oacc[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) oacc[j] = 0;
+#pragma unroll 1
+            for (unsigned k0 = 0; k0 < nnz; k0 += G) {
+                const unsigned k = k0 + g;
+                const int r = (k < nnz) ? sc[k] : -1;
+                const int pc = (k < nnz) ? (int)pq[k] : 0;
+                embed_fast<LPR>(p, wso, lane, p.offC[h], (r >= 0) ? r + 1 : -1, acc, sel);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int c_f = qi_requant(qi_clamp(acc[j], lw), fw, lf, ff);
+                    oacc[j] += qi_mul(pc, c_f, lf, ff);
+                }
+            }
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+                for (int j = 0; j < 16; j++) oacc[j] += __shfl_xor_sync(0xffffffffu, oacc[j], o);
+            if (g == 0) {
+                unsigned packed[4];
+#pragma unroll
+                for (int w4 = 0; w4 < 4; w4++) {
+                    unsigned v = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) v |= ((unsigned)(qi_clamp(oacc[4 * w4 + b], lf) & 0xFF)) << (8 * b);
+                    packed[w4] = v;
+                }
+                *reinterpret_cast<uint4 *>(ovec + 16 * q) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+            __syncwarp();
+
+            // ---- linear map (MemN2N.c:873, layer_cuda.cu:49-68) and update (MemN2N.c:889, layer_cuda.cu:1535) ----
+            const int lw2 = 2 * lw;
+#pragma unroll 1
+            for (unsigned i0 = 0; i0 < d; i0 += 32) {
+                const unsigned i = i0 + lane;
+                int a_f = 0;
+                if (p.lin_map) {
+                    const unsigned hrow = p.offH[h] + min(i, d - 1) * p.HS;
+                    int s_ = 0;
+                    const unsigned d4 = (d + 3) / 4;
+#pragma unroll 2
+                    for (unsigned j4 = 0; j4 < d4; j4++) {
+                        const unsigned hw = *reinterpret_cast<const unsigned *>(smem + hrow + 4u * j4);
+                        const int4 uu = *reinterpret_cast<const int4 *>(ub32 + 4 * j4);
+                        s_ += clamp_biased(shr0m(sbyte_prmt<0>(hw) * uu.x, fb, mb), lw, lw2);
+                        s_ += clamp_biased(shr0m(sbyte_prmt<1>(hw) * uu.y, fb, mb), lw, lw2);
+                        s_ += clamp_biased(shr0m(sbyte_prmt<2>(hw) * uu.z, fb, mb), lw, lw2);
+                        s_ += clamp_biased(shr0m(((int)hw >> 24) * uu.w, fb, mb), lw, lw2);
+                    }
+                    a_f = qi_requant(qi_clamp(s_ - (int)(4u * d4) * lw, lw), fw, lf, ff);
+                } else if (i < d) {
+                    a_f = qi_requant((int)uvec[i], fu, lf, ff);
+                }
+                __syncwarp();
+                if (i < d) uvec[i] = (signed char)qi_clamp(a_f + (int)ovec[i], lf);
+            }
+            fu = ff;
+            __syncwarp();
+        }
+
+        // ---- answer projection, sequential fp32 (MemN2N.c:902-906, layer_cuda.cu:69-82), argmax on the
+        //      probabilities (layer_cuda.cu:1918-1939) ----
+        for (unsigned j = lane; j < DP; j += 32) ufl[j] = (j < d) ? (float)uvec[j] / (float)(1 << fu) : 0.0f;
+        __syncwarp();
+        const unsigned d4 = (d + 3) / 4;
+        float zmax = -INFINITY;
+#pragma unroll 1
+        for (unsigned i0 = 0; i0 < V; i0 += 128) {
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            unsigned wrow[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) wrow[k] = p.offW + min(i0 + 32 * k + lane, V - 1) * (p.WS * 4u);
+#pragma unroll 1
+            for (unsigned j4 = 0; j4 < d4; j4++) {
+                const float4 uu = *reinterpret_cast<const float4 *>(ufl + 4 * j4);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float4 ww = *reinterpret_cast<const float4 *>(smem + wrow[k] + 16u * j4);
+                    z[k] = __fadd_rn(z[k], __fmul_rn(ww.x, uu.x));
+                    z[k] = __fadd_rn(z[k], __fmul_rn(ww.y, uu.y));
+                    z[k] = __fadd_rn(z[k], __fmul_rn(ww.z, uu.z));
+                    z[k] = __fadd_rn(z[k], __fmul_rn(ww.w, uu.w));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned i = i0 + 32 * k + lane;
+                if (i < V) { zbuf[i] = z[k]; zmax = fmaxf(zmax, z[k]); }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+        __syncwarp();
+        // h_i = fl(e_i / total) is monotone in e_i = __expf(z_i - max): only slots whose e is within
+        // 2^-20 of the largest can share the maximal probability; the double total is needed only to
+        // break such near-ties exactly, or when h[y] is requested.
+        unsigned n_cand = 0, cand_idx = 0;
+#pragma unroll 1
+        for (unsigned i0 = 0; i0 < V; i0 += 32) {
+            const unsigned i = i0 + lane;
+            bool cand = false;
+            if (i < V) {
+                const float e = __expf(zbuf[i] - zmax);
+                zbuf[i] = e;
+                cand = (e >= 0.99999905f);
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, cand);
+            if (b) { n_cand += __popc(b); cand_idx = i0 + 31 - __clz(b); }
+        }
+        __syncwarp();
+        unsigned pred_i = cand_idx;
+        float h_true_v = 0.0f;
+        if ((n_cand > 1) || p.want_h) {
+            double total = 0.0;
+#pragma unroll 2
+            for (unsigned i = 0; i < V; i++) total += (double)zbuf[i];
+            float best = -INFINITY;
+            unsigned best_i = 0;
+#pragma unroll 1
+            for (unsigned i0 = 0; i0 < V; i0 += 32) {
+                const unsigned i = i0 + lane;
+                if (i < V) {
+                    const float hv = (float)((double)zbuf[i] / total);
+                    if (!(best > hv)) { best = hv; best_i = i; }
+                    if (i == ans_idx) h_true_v = hv;
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                if (ov > best || (ov == best && oi > best_i)) { best = ov; best_i = oi; }
+            }
+            pred_i = best_i;
+            h_true_v = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(h_true_v)));
+        }
+        if (lane == 0) {
+            if (p.pred) p.pred[story] = pred_i;
+            if (p.h_true) p.h_true[story] = h_true_v;
+            if (p.match && ans_idx != ANS_NONE && pred_i == ans_idx) atomicAdd(p.match, 1u);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace

@@ -47,6 +47,7 @@ void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxe
 }  // namespace qmann
 
 #include "qmann_kernels.cuh"
+#include "qmann_fast.cuh"
 
 namespace {
 
@@ -75,8 +76,11 @@ struct qmann_model {
     unsigned char *dev_rec;
     uint2 *dev_heap;
     unsigned long long heap_cap;
+    // control block (one 32-byte memset per chunk): heap_used u64 | counter | slow_count | counter2
     unsigned long long *dev_heap_used;
-    unsigned *dev_counter, *dev_err;
+    unsigned *dev_counter, *dev_slow_count, *dev_counter2, *dev_err;
+    unsigned *dev_slow_list = nullptr;       // [chunk_cap] chunk indices the fast kernel left to the general one
+    bool fast_ok = false;                    // every weight format has an integer bit (Q_w(1.0) = 2^frac_w)
     unsigned char *dev_colmax = nullptr;     // [V] max |code| per column over all embedding tables (count splitting)
     unsigned nmax = 0;
     // qmann_infer_host staging (grow-only device arenas, two streams)
@@ -129,6 +133,30 @@ int launch_forward(const qmann_model *m, const FwdParams &p, bool debug, cudaStr
         case 8: return launch_forward_l<8>(m, p, debug, st);
         case 16: return launch_forward_l<16>(m, p, debug, st);
         default: return launch_forward_l<32>(m, p, debug, st);
+    }
+}
+
+template <int LPR, int MODE>
+int launch_fast_t(const qmann_model *m, const FwdParams &p, cudaStream_t st)
+{
+    QCUDA(cudaFuncSetAttribute(k_forward_fast<LPR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes));
+    k_forward_fast<LPR, MODE><<<(unsigned)m->sm_count, m->NW * 32, m->smem_bytes, st>>>(p);
+    count_launch();
+    QCUDA(cudaPeekAtLastError());
+    return QMANN_OK;
+}
+template <int LPR>
+int launch_fast_l(const qmann_model *m, const FwdParams &p, cudaStream_t st)
+{
+    return m->cfg.mode == 3 ? launch_fast_t<LPR, 3>(m, p, st) : launch_fast_t<LPR, 2>(m, p, st);
+}
+int launch_fast(const qmann_model *m, const FwdParams &p, cudaStream_t st)
+{
+    switch (m->LPR) {
+        case 4: return launch_fast_l<4>(m, p, st);
+        case 8: return launch_fast_l<8>(m, p, st);
+        case 16: return launch_fast_l<16>(m, p, st);
+        default: return launch_fast_l<32>(m, p, st);
     }
 }
 }  // namespace
@@ -280,6 +308,7 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
             if (c.iwl_w[h] < 1) unit_ok = false;
         }
         m->nmax = unit_ok ? nmax : 0;
+        m->fast_ok = unit_ok;
     }
     QCUDA(cudaPeekAtLastError());
     QCUDA(cudaDeviceSynchronize());
@@ -295,8 +324,11 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     QCUDA(cudaMalloc((void **)&m->dev_rec, (size_t)m->chunk_cap * m->rec_stride));
     m->heap_cap = 8ull << 20;                                        // 8 Mi entries = 64 MiB
     QCUDA(cudaMalloc((void **)&m->dev_heap, m->heap_cap * sizeof(uint2)));
-    QCUDA(cudaMalloc((void **)&m->dev_heap_used, sizeof(unsigned long long)));
-    QCUDA(cudaMalloc((void **)&m->dev_counter, sizeof(unsigned)));
+    QCUDA(cudaMalloc((void **)&m->dev_heap_used, 32));
+    m->dev_counter = reinterpret_cast<unsigned *>(m->dev_heap_used + 1);
+    m->dev_slow_count = m->dev_counter + 1;
+    m->dev_counter2 = m->dev_counter + 2;
+    QCUDA(cudaMalloc((void **)&m->dev_slow_list, (size_t)m->chunk_cap * sizeof(unsigned)));
     QCUDA(cudaMalloc((void **)&m->dev_err, sizeof(unsigned)));
     QCUDA(cudaMemset(m->dev_err, 0, sizeof(unsigned)));
     p.rec = m->dev_rec; p.rec_stride = m->rec_stride; p.off_rend = m->off_rend; p.off_exc = m->off_exc; p.off_ent = m->off_ent;
@@ -309,7 +341,7 @@ void qmann_model_destroy(qmann_model *m)
 {
     if (!m) return;
     cudaFree(m->dev_img); cudaFree(m->dev_rec); cudaFree(m->dev_heap); cudaFree(m->dev_heap_used);
-    cudaFree(m->dev_counter); cudaFree(m->dev_err); cudaFree(m->dev_colmax);
+    cudaFree(m->dev_slow_list); cudaFree(m->dev_err); cudaFree(m->dev_colmax);
     cudaFree(m->e2e_m); cudaFree(m->e2e_q); cudaFree(m->e2e_a); cudaFree(m->e2e_h); cudaFree(m->e2e_pred); cudaFree(m->e2e_match);
     if (m->e2e_compute) cudaStreamDestroy(m->e2e_compute);
     if (m->e2e_copy) cudaStreamDestroy(m->e2e_copy);
@@ -359,8 +391,7 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
         cp.story0 = s0; cp.n_stories = n; cp.rec = m->dev_rec; cp.rec_stride = m->rec_stride; cp.off_rend = m->off_rend;
         cp.off_exc = m->off_exc; cp.off_ent = m->off_ent; cp.lcap = m->lcap; cp.heap = m->dev_heap; cp.heap_cap = m->heap_cap;
         cp.heap_used = m->dev_heap_used; cp.colmax = m->dev_colmax; cp.nmax = m->nmax;
-        QCUDA(cudaMemsetAsync(m->dev_heap_used, 0, sizeof(unsigned long long), st));
-        QCUDA(cudaMemsetAsync(m->dev_counter, 0, sizeof(unsigned), st));
+        QCUDA(cudaMemsetAsync(m->dev_heap_used, 0, 32, st));
         const unsigned cblocks = std::min<unsigned>((n + 7) / 8, (unsigned)m->sm_count * 8);
         cudaEvent_t *pe = nullptr;
         if (m->profile) {
@@ -381,7 +412,15 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
         p.sen_off = b->dev_sen_off; p.story0 = s0; p.n_stories = n; p.n_total = b->N; p.sum_sen = b->sum_sen;
         p.pred = dev_pred; p.h_true = dev_h_true; p.match = dev_match; p.want_h = (dev_h_true != nullptr);
         if (dbg) p.dbg = *dbg;
-        int rc = launch_forward(m, p, debug, st);
+        int rc;
+        if (!debug && m->fast_ok) {
+            // regular stories in the small fast kernel; whatever it declines goes through the general one
+            p.slow_list = m->dev_slow_list; p.slow_count = m->dev_slow_count;
+            rc = launch_fast(m, p, st);
+            if (rc) return rc;
+            p.work_list = m->dev_slow_list; p.work_count = m->dev_slow_count; p.counter = m->dev_counter2;
+        }
+        rc = launch_forward(m, p, debug, st);
         if (rc) return rc;
         if (pe) QCUDA(cudaEventRecord(pe[2], st));
     }

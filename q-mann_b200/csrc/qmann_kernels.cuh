@@ -68,6 +68,10 @@ struct FwdParams {
     unsigned *counter;
     unsigned *err_flag;
     int want_h;
+    // two-pass dispatch: k_forward_fast appends the chunk indices of the stories it does not handle to
+    // slow_list; the general kernel then takes its work from work_list[0 .. *work_count)
+    unsigned *slow_list, *slow_count;
+    const unsigned *work_list, *work_count;
     qmann_debug dbg;
 };
 
@@ -463,6 +467,8 @@ __global__ void __launch_bounds__(512, 1) k_forward(const __grid_constant__ FwdP
     constexpr int G = 32 / LPR;                 // rows embedded concurrently by one warp
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned g = lane / LPR, q = lane % LPR;
+    const unsigned n_work = p.work_count ? *p.work_count : p.n_stories;
+    if (n_work == 0) return;                    // nothing left over by the fast kernel
 
     // ---- stage the quantised tables into shared memory (once per CTA) ----
     {
@@ -502,7 +508,8 @@ __global__ void __launch_bounds__(512, 1) k_forward(const __grid_constant__ FwdP
         unsigned w = 0;
         if (lane == 0) w = atomicAdd(p.counter, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= p.n_stories) break;
+        if (w >= n_work) break;
+        if (p.work_list) w = p.work_list[w];
         const unsigned story = p.story0 + w;
         const unsigned long long soff = p.sen_off[story];
         const unsigned S = (unsigned)(p.sen_off[story + 1] - soff);
