@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- stories/sec of the 3-hop quantized MemN2N inference forward (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C1|C3|C4|C5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
            --master-port P bench.py --gpus N --steps K --warmup W
 
@@ -17,6 +17,10 @@ qmann_infer_host, H2D/D2H inside the timed region), roofline of the dominant ker
 bytes per launch / its CUDA-event duration, against the measured HBM copy bandwidth), cpu_baseline
 (the CPU restatement of the reference on the box's host cores), clocks sampled during the run and
 the number of kernels this library launched in the timed region.
+
+--workload C5 is the other multi-GPU shape (BASELINE.json configs[4]): ONE pre-embedded memory of 2^20 slots,
+d=256, 3 hops, slot-sharded across the ranks (strong scaling: the memory is fixed, every rank streams its
+S/N slots), Q queries per step, two integer all-reduces per hop over NCCL.
 
 --impl reference: the reference has no runnable CPU forward, so this arm times
 the CPU restatement of its CUDA arithmetic (oracle/, kind "port") on all host threads, on a bounded
@@ -145,10 +149,200 @@ def cpu_oracle_rate(synth, cfg, w, S, sample, threads=0):
     return sample / dt, dt, qmo.lib().qmo_max_threads() if threads <= 0 else threads, out
 
 
+# ---------------------------------------------------------------------------------------------------
+# C5: one very large memory, slot-sharded
+# ---------------------------------------------------------------------------------------------------
+C5_S, C5_D, C5_V = 1 << 20, 256, 64
+
+
+def c5_config(synth, mode=2):
+    return synth.ModelConfig(V=C5_V, d=C5_D, S_max=64, V_dict=32, mode=mode)
+
+
+def c5_cpu_rate(synth, cfg, weights, slots=1 << 16, queries=4):
+    """queries/s of the CPU restatement on the FULL memory, extrapolated from the scorer + read over `slots`
+    slots (the cost is linear in the slot count; the per-query tail is included in the timed region)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import qmo_bigmem as qb
+    rng = np.random.default_rng(0x5EED1005)
+    f = cfg.formats()
+    M8 = np.stack([np.clip(np.rint(rng.standard_normal((slots, cfg.d)) * 0.1 * (1 << f["frac_w"][h])), -127, 127).astype(np.int8) for h in range(cfg.H)])
+    C8 = np.stack([np.clip(np.rint(rng.standard_normal((slots, cfg.d)) * 0.5 * (1 << f["frac_w"][h])), -127, 127).astype(np.int8) for h in range(cfg.H)])
+    u0 = np.clip(np.rint(rng.standard_normal((queries, cfg.d)) * 3), -127, 127).astype(np.int8)
+    t0 = time.perf_counter()
+    qb.forward(cfg, weights, M8, C8, u0)
+    dt = time.perf_counter() - t0
+    per_query_full = dt / queries * (C5_S / slots)
+    return 1.0 / per_query_full, dt, slots, queries
+
+
+def run_bigmem(args):
+    import torch
+    rank, world, local = dist_setup(args.gpus)
+    if world == 1 and args.gpus > 1:
+        print("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    pkg = ge.import_package()
+    synth, qlib = pkg.synth, pkg.lib
+    cfg = c5_config(synth)
+    Q = args.queries
+    W, K = max(3, args.warmup), max(1, args.steps)
+    weights = synth.make_weights(cfg, 0x5EED0000 + 5, sigma=0.3)
+    f = cfg.formats()
+    lo, n_loc = qlib.slot_shard(C5_S, world, rank)
+    # the memory is generated on the device, shard by shard, from a seed that depends only on (hop, slot block),
+    # so the global memory is the same for every world size
+    BLK = 1 << 16
+    def gen(kind, h):
+        out = torch.empty((n_loc, cfg.d), dtype=torch.int8, device=dev)
+        sc = (0.1 if kind == 0 else 0.5) * (1 << f["frac_w"][h])
+        for b0 in range(lo // BLK * BLK, lo + n_loc, BLK):
+            g = torch.Generator(device=dev).manual_seed(0x5EED1000 + 7919 * (b0 // BLK) + 131 * h + kind)
+            blk = (torch.randn((BLK, cfg.d), device=dev, generator=g) * sc).round().clamp(-127, 127).to(torch.int8)
+            a, b = max(b0, lo), min(b0 + BLK, lo + n_loc)
+            out[a - lo:b - lo] = blk[a - b0:b - b0]
+        return out
+    M8 = [gen(0, h) for h in range(cfg.H)]
+    C8 = [gen(1, h) for h in range(cfg.H)]
+    gq = torch.Generator(device=dev).manual_seed(0x5EED2000)
+    u0 = (torch.randn((Q, cfg.d), device=dev, generator=gq) * 3).round().clamp(-127, 127).to(torch.int8)
+    # plant one strongly matching slot per query in hop 0 so that the weighted read is not empty
+    for q in range(Q):
+        r = (q * 104729 + 17) % C5_S
+        if lo <= r < lo + n_loc:
+            M8[0][r - lo] = (u0[q].to(torch.int32) * 2).clamp(-127, 127).to(torch.int8)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        group = dist.group.WORLD
+    mem = qlib.BigMemory(cfg, weights, M8, C8, C5_S, lo, Q_max=Q, device=dev, group=group, world=world)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        mem.forward(u0)
+    barrier()
+    mem.profile(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = qlib.lib().qmann_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(K):
+        out = mem.forward(u0)
+        mem.profile_read()              # folds this step's event pairs (waits for its score kernels only)
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = qlib.lib().qmann_launch_count() - launches0
+    ms_scores, n_scores = mem.profile_read(reset=True)
+    mem.profile(False)
+    t_end = time.time() + max(0.0, 0.6 - ms_total / 1e3)
+    while time.time() < t_end:
+        mem.forward(u0)
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    pred_dev = out["pred"].cpu().numpy().copy()
+
+    # end to end: pinned host queries in, host predictions out
+    u0_pin = u0.cpu().pin_memory()
+    pred_pin = torch.empty(Q, dtype=torch.int32).pin_memory()
+    u0_stage = torch.empty_like(u0)
+    Ke = args.e2e_steps or min(K, 8)
+
+    def e2e_step():
+        u0_stage.copy_(u0_pin, non_blocking=True)
+        o = mem.forward(u0_stage)
+        pred_pin.copy_(o["pred"], non_blocking=True)
+        torch.cuda.synchronize()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / Ke
+    assert np.array_equal(pred_pin.numpy(), pred_dev)
+
+    ms_step = ms_total / K
+    k_scores_ms = ms_scores / max(1, n_scores)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_step, e2e_ms, k_scores_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms, k_scores_ms = float(t[0]), float(t[1]), float(t[2])
+    if rank == 0:
+        value = Q / (ms_step / 1e3)
+        peak, peak_src = measured_peak()
+        bytes_launch = n_loc * cfg.d                     # one hop's M shard, int8, read once per launch
+        achieved = bytes_launch / (k_scores_ms / 1e3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, dt, slots, qs = c5_cpu_rate(synth, cfg, weights)
+            cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{qs} queries x {slots} of the 2^20 slots in {dt:.1f} s (oracle/qmo_bigmem.py over qmann_oracle.c), "
+                             "scaled linearly in the slot count to the full memory"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": f"C5: one pre-embedded memory of 2^20 slots, d=256, 3 hops, fixed-point dot attention, {Q} queries per step "
+                                   "(a story = one query against the whole memory)",
+                       "memory": "int8 codes M_h, C_h per hop (1.61 GB), N(0,0.1)/N(0,0.5) quantised in the EN_MQ formats, resident in HBM",
+                       "l2": f"{n_loc * cfg.d / 1e6:.0f} MB of M per hop and rank; three different hops' memories are streamed per step "
+                             f"({3 * n_loc * cfg.d / 1e6:.0f} MB" + (", larger than the 126 MB L2)" if 3 * n_loc * cfg.d > 126e6 else ", smaller than the 126 MB L2: query blocks after the first hit L2)"),
+                       "parallelism": f"slot-sharded x{world}; per hop all_reduce(SUM) of u32 score histograms [Q][255] and i32 partial reads [Q][256] over NCCL"},
+            "e2e": {"value": Q / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(Q * cfg.d), "d2h_bytes_per_step": int(4 * Q),
+                    "ms_per_step": e2e_ms, "steps": Ke, "api": "qmann_bigmem_* phases (pinned host queries in, host predictions out)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_big_scores", "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
+                         "algorithmic_bytes_per_launch": bytes_launch, "launch_ms": k_scores_ms,
+                         "note": "one launch streams one hop's M shard (S_local*d int8) for all Q queries; the C rows are a sparse gather of the "
+                                 "<= 2^frac slots whose quantised attention weight is non-zero, so they are not streamed; with Q > 1 the kernel is "
+                                 "INT-issue bound (Q*S*d quantised products), not HBM bound"},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def run_reference(args):
     """--impl reference: CPU restatement of the reference (kind "port"), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return 0
+    if args.workload == "C5":
+        pkg = ge.import_package()
+        cfg = c5_config(pkg.synth)
+        weights = pkg.synth.make_weights(cfg, 0x5EED0000 + 5, sigma=0.3)
+        rates = []
+        for i in range(args.warmup + args.steps):
+            rate, dt, slots, qs = c5_cpu_rate(pkg.synth, cfg, weights)
+            if i >= args.warmup:
+                rates.append((rate, dt))
+        value = float(np.mean([r for r, _ in rates]))
+        ms = 1e3 * float(np.mean([d for _, d in rates]))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": f"C5: one pre-embedded memory of 2^20 slots, d=256, 3 hops; {qs} queries x {slots} slots per step, scaled to the full memory"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{qs} queries x {slots} of 2^20 slots per step (oracle/qmo_bigmem.py), scaled linearly in the slot count"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return 0
     pkg = ge.import_package()
     synth = pkg.synth
@@ -187,12 +381,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--queries", type=int, default=64, help="C5: queries per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "C5":
+        return run_bigmem(args)
 
     import torch
     rank, world, local = dist_setup(args.gpus)

@@ -220,6 +220,53 @@ int  qmann_shard_plan(const uint32_t *n_sen, uint32_t N, uint32_t world, uint32_
 int  qmann_profile_enable(qmann_model *m, int enable);
 int  qmann_profile_read(qmann_model *m, float *ms_compact, float *ms_forward, uint32_t *n_pairs);
 
+/* ============================================================================================
+ * Part 3 -- one very large pre-embedded memory, slot-sharded across GPUs (BASELINE config 5).
+ * The reference cannot launch this shape (every dimension is capped at 1024 by its <<<d, S>>> launches,
+ * lib/layer_cuda.cu:547-559); the arithmetic per slot is the reference's (scorer lib/layer_cuda.cu:105-141 /
+ * :355-541, softmax :1969-2060, weighted read :547-579, linear map :49-68, update :1535-1542).
+ *
+ * Each rank (one process per GPU) owns S_local contiguous slots [slot0, slot0+S_local) of S_total.  A hop is
+ * three calls with one collective after each of the first two (issued by the caller, e.g. torch.distributed
+ * all_reduce over NCCL, on the same stream):
+ *     qmann_bigmem_hop_scores(h, dev_hist)              local scores + local per-query score histogram
+ *         all-reduce SUM of dev_hist   (uint32 [Q][qmann_bigmem_num_bins()])
+ *     qmann_bigmem_hop_read(h, dev_hist, dev_partial)   global max/total from the histogram (identical on every
+ *                                                       rank, fixed summation order), Q_f(p), local partial read
+ *         all-reduce SUM of dev_partial (int32 [Q][d])
+ *     qmann_bigmem_hop_update(h, dev_partial)           final clamp, linear map, u_{h+1} = u_h (+) o_h
+ * With one rank the collectives are simply skipped.  The result does not depend on the number of shards.
+ * ========================================================================================== */
+typedef struct qmann_bigmem qmann_bigmem;
+
+/* dev_M[h], dev_C[h]: int8 codes [S_local][d] in hop h's weight format (iwl_w[h], frac_w[h]) -- what
+ * emb_m[h] / emb_c[h] output (MemN2N.c:835-838); not copied, must outlive the object.  w: only dev_Hm[h]
+ * (fp32 [d][d], if cfg.lin_map) and dev_W (fp32 [V][d], may be NULL with cfg.V == 0) are used.
+ * d must be a multiple of 16; cfg.S_max is ignored. */
+int  qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann_weights *w,
+                         const int8_t *const *dev_M, const int8_t *const *dev_C,
+                         uint64_t S_total, uint64_t slot0, uint64_t S_local, uint32_t Q_max);
+void qmann_bigmem_destroy(qmann_bigmem *b);
+uint32_t qmann_bigmem_num_bins(const qmann_bigmem *b);
+/* Start a batch of Q queries: dev_u0 int8 [Q][d], codes in the hop-0 weight format (the output of emb_q). */
+int  qmann_bigmem_begin(qmann_bigmem *b, const int8_t *dev_u0, uint32_t Q, void *stream);
+int  qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, void *stream);
+/* dev_pbin: optional fp32 [Q][num_bins] attention weight per score bin (parity checks), else NULL */
+int  qmann_bigmem_hop_read(qmann_bigmem *b, uint32_t h, const uint32_t *dev_hist, int32_t *dev_partial,
+                           float *dev_pbin, void *stream);
+/* dev_o, dev_g: optional int8 [Q][d] dumps of the read and of the linear-map output, else NULL */
+int  qmann_bigmem_hop_update(qmann_bigmem *b, uint32_t h, const int32_t *dev_partial, int8_t *dev_o, int8_t *dev_g,
+                             void *stream);
+/* Current controller state u: int8 codes [Q][d] and their fractional bits. */
+int  qmann_bigmem_state(qmann_bigmem *b, int8_t *dev_u, int32_t *frac_bits, void *stream);
+/* Answer projection (fp32, index order), softmax, argmax_last.  dev_z/dev_h: optional fp32 [Q][V]. */
+int  qmann_bigmem_finish(qmann_bigmem *b, uint32_t *dev_pred, float *dev_z, float *dev_h, void *stream);
+/* Optional CUDA-event timing of the dominant kernel (k_big_scores, one launch per hop).  _read folds the pending
+ * event pairs (at most one forward's worth: call it after every forward while enabled), synchronising on them. */
+int  qmann_bigmem_profile_enable(qmann_bigmem *b, int enable);
+int  qmann_bigmem_profile_read(qmann_bigmem *b, float *ms_scores, uint32_t *n_launches, int reset);
+const char *qmann_bigmem_last_error(void);
+
 /* Number of kernel launches issued by this library since load (for benchmarks' accounting). */
 uint64_t qmann_launch_count(void);
 const char *qmann_last_error(void);

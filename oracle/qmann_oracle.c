@@ -281,6 +281,13 @@ void qmo_softmax(const float *in, float *out, uint32_t dim)
     for (uint32_t i = 0; i < dim; i++) out[i] = (float)(out[i] / total);
 }
 
+/* out[i] = expf(in[i] - mx): the exponentials of _cuda_softmax_fwd (device: __expf), exposed so that the
+ * large-memory restatement (oracle/qmo_bigmem.py) uses the same libm expf as qmo_softmax */
+void qmo_expf_shifted(const float *in, float mx, float *out, uint32_t dim)
+{
+    for (uint32_t i = 0; i < dim; i++) out[i] = expf(in[i] - mx);
+}
+
 /* _cuda_vec_vec_sum<<<1,dim>>>                                         layer_cuda.cu:1535-1542 */
 void qmo_vec_vec_sum(const float *a, const float *b, float *out, uint32_t dim, int f_fixed, qmo_fmt f)
 {

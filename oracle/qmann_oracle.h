@@ -111,6 +111,7 @@ void qmo_mat_trans_mat_product(const float *p, const float *Cm, float *out, uint
 void qmo_approximate_attention(const float *M, const float *u, float *out, uint32_t S, uint32_t d,
                                uint32_t iwl, uint32_t num_bit, int32_t const_scale);
 void qmo_softmax(const float *in, float *out, uint32_t dim);
+void qmo_expf_shifted(const float *in, float mx, float *out, uint32_t dim);
 void qmo_vec_vec_sum(const float *a, const float *b, float *out, uint32_t dim, int f_fixed, qmo_fmt f);
 uint32_t qmo_argmax_last(const float *in, uint32_t dim);
 

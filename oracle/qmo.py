@@ -74,6 +74,8 @@ def lib():
         L.qmo_appx_element.argtypes = [C.c_float, C.c_float, C.c_uint32, C.c_uint32]
         L.qmo_softmax.restype = None
         L.qmo_softmax.argtypes = [_FP, _FP, C.c_uint32]
+        L.qmo_expf_shifted.restype = None
+        L.qmo_expf_shifted.argtypes = [_FP, C.c_float, _FP, C.c_uint32]
         L.qmo_argmax_last.restype = C.c_uint32
         L.qmo_argmax_last.argtypes = [_FP, C.c_uint32]
         L.qmo_mat_vec_product.restype = None

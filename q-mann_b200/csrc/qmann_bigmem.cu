@@ -1,0 +1,722 @@
+// qmann_bigmem.cu -- memory addressing over ONE very large pre-embedded memory (BASELINE config 5:
+// >= 1M slots, d = 256, 3 hops), slot-sharded across GPUs (include/qmann_abi.h part 3).
+//
+// The reference cannot run this shape (its <<<d, S>>> launches and temp[1024] cap every dimension at
+// 1024, lib/layer_cuda.cu:547-559, lib/layer_cuda.h:11); the arithmetic is the reference's, applied to
+// a memory whose rows M_h[r][:], C_h[r][:] are given as the int8 codes emb_m[h]/emb_c[h] would output
+// (MemN2N/MemN2N.c:835-838), for Q queries at once.
+//
+// Per hop, per rank (this rank owns S_local contiguous slots):
+//   k_big_scores   streams M_h once (HBM), lane-per-slot, QB queries register-blocked per pass:
+//                  s[r] = Q_att(sum_t Q_att(Q_att(M[r][t]) * Q_bin(u[t])))        layer_cuda.cu:105-141
+//                  or the Hamming/approximate similarity                          layer_cuda.cu:355-541
+//                  -> 16-bit score bins [Q][S_local]
+//   k_big_hist     per-query histogram of the score bins (shared-memory atomics)
+//        ---- all-reduce(SUM, u32) of the histograms across ranks (NCCL, by the caller) ----
+//   k_big_softmax  every rank rebuilds the SAME max and double-precision total from the global
+//                  histogram in a fixed order (bins ascending, 256 contiguous ranges, range partials
+//                  added ascending), p_bin = fl32(__expf(v_bin - max) / total), Q_f(p_bin)
+//                                                                                layer_cuda.cu:1969-2060, :561
+//   k_big_read     scans the score bins; only slots with Q_f(p) != 0 (at most 2^frac of them, because
+//                  sum p = 1) contribute Q_f(Q_f(p) * Q_f(C[r][c])) to the read: a sparse gather of C
+//                  rows into an int32 partial read                                layer_cuda.cu:547-579
+//        ---- all-reduce(SUM, i32) of the partial reads [Q][d] ----
+//   k_big_update   o = Q_f(sum), g = linear map, u' = Q_f(Q_f(g) + Q_f(o))        layer_cuda.cu:49-68, 1535
+// and after the last hop k_big_answer (fp32 projection in index order, softmax, argmax_last).
+//
+// A log-sum-exp merge of locally normalised reads would NOT be exact: Q_f(p) truncates, so every
+// shard must quantise with the global max and total (hard part 3).  The integer
+// histogram makes that a single exact collective and the result independent of the number of shards.
+#include "qmann_fixed.cuh"
+#include "qmann_common.h"
+#include "../../include/qmann_abi.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+using namespace qmann;
+
+namespace {
+
+thread_local std::string g_berr;
+int bfail(int code, const std::string &msg) { g_berr = msg; return code; }
+#define BCUDA(expr)                                                                                \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) return bfail(QMANN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+constexpr int MAXH = QMANN_MAX_HOP;
+constexpr unsigned SOFTMAX_RANGES = 256;       // fixed summation order of k_big_softmax
+
+struct HopFmt {
+    int fw, lw, fa, la, ia, ff, lf, iff, fb, lb;
+};
+
+// -------------------------------------------------------------------------------------------------
+// query preparation: u (int8 codes, fu fractional bits) -> operands of the scorer
+//   mode 2: ub[q][t] = Q_bin(u) as int32                                          MemN2N.c:847
+//   mode 3: av[q][t] = 31-bit magnitude, sv[q][t] = sign word                      layer.c:215-233
+// -------------------------------------------------------------------------------------------------
+__global__ void k_big_prep_query(const signed char *__restrict__ u, int fu, unsigned Q, unsigned d, int mode, HopFmt f,
+                                 int *__restrict__ ub, unsigned *__restrict__ av, unsigned *__restrict__ sv)
+{
+    const size_t n = (size_t)Q * d;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)u[i];
+        ub[i] = qi_requant(c, fu, f.lb, f.fb);
+        if (mode == 3) {
+            unsigned s_, m_;
+            appx_encode(c, fu, f.ia, s_, m_);
+            av[i] = m_;
+            sv[i] = s_;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_big_scores: lane-per-slot.  A warp stages 32 memory rows (32*d bytes, coalesced 128-bit loads)
+// into its shared-memory tile with a row stride of d+16 bytes (conflict-free 128-bit lane-per-row
+// reads), then every lane walks its own row in 16-dim chunks against QB queries whose operands are
+// broadcast from shared memory.
+// -------------------------------------------------------------------------------------------------
+struct ScoreParams {
+    const signed char *M;           // [S_local][d] codes of this hop, weight format
+    unsigned long long S_local;
+    unsigned d, Q;
+    HopFmt f;
+    int const_scale;
+    const int *ub;                  // [Q][d]
+    const unsigned *av, *sv;        // [Q][d] (mode 3)
+    unsigned short *bins;           // [Q][S_local] score bin = code + bias
+    unsigned bias;                  // la (mode 2) or 127*d (mode 3)
+};
+
+__device__ __forceinline__ int sx8(unsigned w, int b) { return (int)(signed char)((w >> (8 * b)) & 0xFFu); }
+
+template <int MODE, int QB>
+__global__ void __launch_bounds__(256) k_big_scores(const ScoreParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned d = p.d, rs = d + 16;                    // tile row stride (bytes)
+    const unsigned q0 = blockIdx.y * QB;
+    const unsigned nq = min((unsigned)QB, p.Q - q0);
+    // query operands of this block of queries: [QB][d] int32 (+ [QB][d] magnitudes and signs in mode 3)
+    int *ubs = reinterpret_cast<int *>(sm);
+    unsigned *avs = reinterpret_cast<unsigned *>(sm + (size_t)QB * d * 4);
+    unsigned *svs = avs + (size_t)QB * d;
+    const size_t qbytes = (size_t)QB * d * 4 * (MODE == 3 ? 3 : 1);
+    unsigned char *tile = sm + qbytes + (size_t)wid * 32 * rs;
+    for (unsigned i = threadIdx.x; i < QB * d; i += blockDim.x) {
+        const unsigned q = i / d, t = i % d;
+        const bool ok = q < nq;
+        ubs[i] = ok ? p.ub[(size_t)(q0 + q) * d + t] : 0;
+        if (MODE == 3) {
+            avs[i] = ok ? p.av[(size_t)(q0 + q) * d + t] : 0u;
+            svs[i] = ok ? p.sv[(size_t)(q0 + q) * d + t] : 0u;
+        }
+    }
+    __syncthreads();
+
+    const HopFmt f = p.f;
+    const int mb = (1 << f.fb) - 1;
+    const unsigned c16 = d / 16;                            // 16-byte chunks per row
+    const unsigned long long n_tiles = (p.S_local + 31) / 32;
+    for (unsigned long long tix = (unsigned long long)blockIdx.x * nw + wid; tix < n_tiles; tix += (unsigned long long)gridDim.x * nw) {
+        const unsigned long long slot0 = tix * 32;
+        // ---- stage 32 rows ----
+        const unsigned total16 = 32 * c16;
+#pragma unroll 4
+        for (unsigned i = lane; i < total16; i += 32) {
+            const unsigned r = i / c16, c = i % c16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (slot0 + r < p.S_local) v = __ldg(reinterpret_cast<const uint4 *>(p.M + (slot0 + r) * d) + c);
+            *reinterpret_cast<uint4 *>(tile + r * rs + c * 16) = v;
+        }
+        __syncwarp();
+        // ---- lane-per-slot scoring ----
+        int acc[QB];
+#pragma unroll
+        for (int q = 0; q < QB; q++) acc[q] = 0;
+        const unsigned char *row = tile + lane * rs;
+        for (unsigned c = 0; c < c16; c++) {
+            const uint4 w4 = *reinterpret_cast<const uint4 *>(row + c * 16);
+            const unsigned ww[4] = {w4.x, w4.y, w4.z, w4.w};
+            int m[16];
+            unsigned am[16], smb = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int code = sx8(ww[j >> 2], j & 3);
+                if (MODE == 3) {
+                    unsigned s_, m_;
+                    appx_encode(code, f.fw, f.ia, s_, m_);
+                    am[j] = m_;
+                    smb |= (s_ >> 31) << j;
+                    m[j] = 0;
+                } else {
+                    m[j] = qi_requant(code, f.fw, f.la, f.fa);         // Q_att(M)
+                    am[j] = 0;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < QB; q++) {
+                int part = 0;
+                if (MODE == 3) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        const uint4 a4 = *reinterpret_cast<const uint4 *>(avs + (size_t)q * d + c * 16 + j4 * 4);
+                        const uint4 s4 = *reinterpret_cast<const uint4 *>(svs + (size_t)q * d + c * 16 + j4 * 4);
+                        const unsigned aa[4] = {a4.x, a4.y, a4.z, a4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int j = j4 * 4 + k;
+                            part += appx_element_x128(((smb >> j) & 1u) << 31, am[j], ss[k], aa[k]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        const int4 u4 = *reinterpret_cast<const int4 *>(ubs + (size_t)q * d + c * 16 + j4 * 4);
+                        const int uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int x = m[j4 * 4 + k] * uu[k];
+                            const int t = (int)((unsigned)x >> 31) * mb + x >> f.fb;      // trunc toward zero
+                            part += __viaddmin_s32_relu(t, f.la, 2 * f.la);                 // clamp + la
+                        }
+                    }
+                    part -= 16 * f.la;
+                }
+                acc[q] += part;
+            }
+        }
+        __syncwarp();
+        if (slot0 + lane < p.S_local) {
+#pragma unroll
+            for (int q = 0; q < QB; q++) {
+                if ((unsigned)q < nq) {
+                    // mode 2: Q_att of the sum; mode 3: the raw sum of e*128 (saturation is applied where the
+                    // value is formed, in k_big_softmax)
+                    const int code = (MODE == 3) ? acc[q] : qi_clamp(acc[q], f.la);
+                    p.bins[(size_t)(q0 + q) * p.S_local + slot0 + lane] = (unsigned short)(code + (int)p.bias);
+                }
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_big_hist: hist[q][bin] += count over this rank's slots.  Small bin counts (mode 2: 255) live in
+// shared memory; large ones (mode 3: 2*127*d+1) use warp-aggregated global atomics.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_big_hist(const unsigned short *__restrict__ bins, unsigned long long S_local, unsigned NB,
+                                                  unsigned *__restrict__ hist, int use_smem)
+{
+    extern __shared__ unsigned hs[];
+    const unsigned q = blockIdx.y;
+    const unsigned short *b = bins + (size_t)q * S_local;
+    unsigned *hq = hist + (size_t)q * NB;
+    if (use_smem) {
+        for (unsigned i = threadIdx.x; i < NB; i += blockDim.x) hs[i] = 0;
+        __syncthreads();
+    }
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < S_local; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned v = b[i];
+        if (use_smem) {
+            atomicAdd(&hs[v], 1u);
+        } else {
+            const unsigned act = __activemask();
+            const unsigned peers = __match_any_sync(act, v);
+            if ((threadIdx.x & 31) == (unsigned)(__ffs((int)peers) - 1)) atomicAdd(&hq[v], (unsigned)__popc(peers));
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < NB; i += blockDim.x)
+            if (hs[i]) atomicAdd(&hq[i], hs[i]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_big_softmax: one CTA per query.  From the GLOBAL histogram: max bin, total, Q_f(p) per bin.
+// value(bin): mode 2 (bin - la) / 2^fa; mode 3 Q_(iwl,31-iwl)((bin - 127 d) / 2^(7 - const_scale))
+// with the +-2^iwl saturation and the -2^iwl -> 0 quirk.
+// -------------------------------------------------------------------------------------------------
+struct SoftmaxParams {
+    const unsigned *hist;      // [Q][NB] global counts
+    unsigned NB, bias;
+    int mode, fa, ia, const_scale, iff, ff;
+    unsigned char *pq;         // [Q][NB] Q_f(p) code per bin (0 where the bin is empty)
+    unsigned *thr;             // [Q] lowest bin with a non-zero code (NB if none)
+    float *pbin;               // optional [Q][NB] p per bin (parity checks)
+    double *total_out;         // optional [Q]
+};
+
+__device__ __forceinline__ float big_bin_value(const SoftmaxParams &p, unsigned bin)
+{
+    const int n = (int)bin - (int)p.bias;
+    if (p.mode == 3) {
+        const float v = (float)n / (float)(1 << (7 - p.const_scale));
+        const float lim = (float)(1 << p.ia);
+        return (v >= lim) ? lim : (v < -lim ? -lim : (v == -lim ? 0.0f : v));
+    }
+    return (float)n / (float)(1 << p.fa);
+}
+
+__global__ void __launch_bounds__(SOFTMAX_RANGES) k_big_softmax(const SoftmaxParams p)
+{
+    __shared__ float s_max[SOFTMAX_RANGES];
+    __shared__ double s_part[SOFTMAX_RANGES];
+    __shared__ double s_total;
+    __shared__ unsigned s_thr;
+    const unsigned q = blockIdx.x, t = threadIdx.x;
+    const unsigned *h = p.hist + (size_t)q * p.NB;
+    const unsigned per = (p.NB + SOFTMAX_RANGES - 1) / SOFTMAX_RANGES;
+    const unsigned b0 = min(p.NB, t * per), b1 = min(p.NB, b0 + per);
+    // max over non-empty bins (mode 3 values are not monotone in the bin at the saturation edge, so take
+    // the max of the VALUES, like _cuda_max does on the score vector, layer_cuda.cu:1895-1916)
+    float mx = -INFINITY;
+    for (unsigned b = b0; b < b1; b++)
+        if (h[b]) mx = fmaxf(mx, big_bin_value(p, b));
+    s_max[t] = mx;
+    __syncthreads();
+    if (t == 0) {
+        float m = -INFINITY;
+        for (unsigned i = 0; i < SOFTMAX_RANGES; i++) m = fmaxf(m, s_max[i]);
+        s_max[0] = m;
+        s_thr = p.NB;
+    }
+    __syncthreads();
+    mx = s_max[0];
+    // total = sum_bins count * __expf(v - max): each range ascending, then the range partials ascending
+    double part = 0.0;
+    for (unsigned b = b0; b < b1; b++)
+        if (h[b]) part += (double)h[b] * (double)__expf(big_bin_value(p, b) - mx);
+    s_part[t] = part;
+    __syncthreads();
+    if (t == 0) {
+        double tot = 0.0;
+        for (unsigned i = 0; i < SOFTMAX_RANGES; i++) tot += s_part[i];
+        s_total = tot;
+        if (p.total_out) p.total_out[q] = tot;
+    }
+    __syncthreads();
+    const double total = s_total;
+    unsigned lo = p.NB;
+    for (unsigned b = b0; b < b1; b++) {
+        unsigned code = 0;
+        float pr = 0.0f;
+        if (h[b]) {
+            pr = (float)((double)__expf(big_bin_value(p, b) - mx) / total);
+            code = (unsigned)qi_encode(pr, p.iff, p.ff);                       // layer_cuda.cu:561
+            if (code && b < lo) lo = b;
+        }
+        p.pq[(size_t)q * p.NB + b] = (unsigned char)code;
+        if (p.pbin) p.pbin[(size_t)q * p.NB + b] = pr;
+    }
+    if (lo < p.NB) atomicMin(&s_thr, lo);
+    __syncthreads();
+    if (t == 0) p.thr[q] = s_thr;
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_big_read: partial[q][c] += Q_f( Q_f(p[r]) * Q_f(C[r][c]) ) over this rank's slots with Q_f(p) != 0.
+// The test is on the code itself (pq[bin] != 0; in mode 3 the value is not monotone in the bin at the
+// -2^iwl edge); thr[] = lowest bin with a non-zero code skips the table lookup for almost every slot.
+// -------------------------------------------------------------------------------------------------
+struct ReadParams {
+    const unsigned short *bins;
+    const unsigned char *pq;
+    const unsigned *thr;
+    const signed char *C;
+    unsigned long long S_local;
+    unsigned NB, d;
+    HopFmt f;
+    int *partial;               // [Q][d]
+    unsigned *nsel;             // optional [Q]: number of selected slots (diagnostics)
+};
+
+__global__ void __launch_bounds__(256) k_big_read(const ReadParams p)
+{
+    const unsigned q = blockIdx.y, lane = threadIdx.x & 31;
+    const unsigned short *b = p.bins + (size_t)q * p.S_local;
+    const unsigned char *pq = p.pq + (size_t)q * p.NB;
+    const unsigned thr = p.thr[q];
+    if (thr >= p.NB) return;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long n_iter = (p.S_local + stride - 1) / stride;
+    for (unsigned long long it = 0; it < n_iter; it++) {
+        const unsigned long long i = it * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+        unsigned code = 0;
+        if (i < p.S_local) {
+            const unsigned v = b[i];
+            if (v >= thr) code = pq[v];                       // thr = lowest bin whose code is non-zero
+        }
+        unsigned hits = __ballot_sync(0xffffffffu, code != 0u);
+        while (hits) {
+            const unsigned src = (unsigned)(__ffs((int)hits) - 1);
+            hits &= hits - 1u;
+            const unsigned long long slot = __shfl_sync(0xffffffffu, i, src);
+            const int pc = (int)__shfl_sync(0xffffffffu, code, src);
+            const signed char *crow = p.C + slot * p.d;
+            for (unsigned c = lane; c < p.d; c += 32) {
+                const int c_f = qi_requant((int)crow[c], p.f.fw, p.f.lf, p.f.ff);
+                const int term = qi_mul(pc, c_f, p.f.lf, p.f.ff);
+                if (term) atomicAdd(&p.partial[(size_t)q * p.d + c], term);
+            }
+            if (p.nsel && lane == 0) atomicAdd(&p.nsel[q], 1u);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_big_update: one CTA per query.  o = Q_f(partial sum); g = Q_w(sum_j Q_w(Q_w(Hm[i][j]) * Q_bin(u[j])));
+// u' = Q_f(Q_f(g) + Q_f(o))                                   MemN2N.c:873,889; layer_cuda.cu:49-68, 1535
+// -------------------------------------------------------------------------------------------------
+struct UpdateParams {
+    const int *partial;          // [Q][d] (summed over ranks)
+    const signed char *u_in;     // [Q][d], fu fractional bits
+    signed char *u_out;          // [Q][d], ff fractional bits
+    const int *ub;               // [Q][d] Q_bin(u)
+    const signed char *Hq;       // [d][d] codes of Hm in the hop's weight format (NULL: no linear map)
+    unsigned d;
+    int fu;
+    HopFmt f;
+    signed char *dbg_o, *dbg_g;  // optional [Q][d]
+};
+
+__global__ void __launch_bounds__(256) k_big_update(const UpdateParams p)
+{
+    const unsigned q = blockIdx.x;
+    const HopFmt f = p.f;
+    for (unsigned i = threadIdx.x; i < p.d; i += blockDim.x) {
+        const int o = qi_clamp(p.partial[(size_t)q * p.d + i], f.lf);
+        int a_f, g_w;
+        if (p.Hq) {
+            int s = 0;
+            for (unsigned j = 0; j < p.d; j++) s += qi_mul((int)p.Hq[(size_t)i * p.d + j], p.ub[(size_t)q * p.d + j], f.lw, f.fb);
+            g_w = qi_clamp(s, f.lw);
+            a_f = qi_requant(g_w, f.fw, f.lf, f.ff);
+        } else {
+            g_w = (int)p.u_in[(size_t)q * p.d + i];
+            a_f = qi_requant(g_w, p.fu, f.lf, f.ff);
+        }
+        p.u_out[(size_t)q * p.d + i] = (signed char)qi_clamp(a_f + o, f.lf);
+        if (p.dbg_o) p.dbg_o[(size_t)q * p.d + i] = (signed char)o;
+        if (p.dbg_g) p.dbg_g[(size_t)q * p.d + i] = (signed char)g_w;
+    }
+}
+
+__global__ void k_big_quant_H(const float *__restrict__ w, signed char *__restrict__ out, unsigned n, int iwl, int frac)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (signed char)qi_encode(w[i], iwl, frac);
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_big_answer: one warp per query.  z[i] = sum_j fl(W[i][j] * u[j]) sequential fp32 (MemN2N.c:902-906,
+// layer_cuda.cu:69-82), softmax with the sequential double total, argmax_last on the probabilities
+// (layer_cuda.cu:1918-1939).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_big_answer(const float *__restrict__ W, const signed char *__restrict__ u, int fu, unsigned Q, unsigned V,
+                                                    unsigned d, float *__restrict__ zbuf, unsigned *__restrict__ pred, float *__restrict__ hout)
+{
+    const unsigned q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    float *z = zbuf + (size_t)q * V;
+    const float inv = 1.0f / (float)(1 << fu);
+    float zmax = -INFINITY;
+    for (unsigned i = lane; i < V; i += 32) {
+        float acc = 0.0f;
+        for (unsigned j = 0; j < d; j++) acc = __fadd_rn(acc, __fmul_rn(W[(size_t)i * d + j], (float)u[(size_t)q * d + j] * inv));
+        z[i] = acc;
+        zmax = fmaxf(zmax, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+    __syncwarp();
+    double total = 0.0;
+    for (unsigned i = 0; i < V; i++) total += (double)__expf(z[i] - zmax);
+    float best = -INFINITY;
+    unsigned best_i = 0;
+    for (unsigned i = lane; i < V; i += 32) {
+        const float hv = (float)((double)__expf(z[i] - zmax) / total);
+        if (hout) hout[(size_t)q * V + i] = hv;
+        if (!(best > hv)) { best = hv; best_i = i; }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const unsigned oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi > best_i)) { best = ov; best_i = oi; }
+    }
+    if (lane == 0 && pred) pred[q] = best_i;
+}
+
+}  // namespace
+
+// =================================================================================================
+// host object
+// =================================================================================================
+struct qmann_bigmem {
+    qmann_config cfg;
+    int sm_count;
+    const signed char *M[MAXH], *C[MAXH];
+    unsigned long long S_total, slot0, S_local;
+    unsigned Q_max, Q, NB, bias;
+    HopFmt f[MAXH];
+    signed char *dev_H[MAXH];
+    const float *dev_W;
+    // work buffers
+    signed char *u_a, *u_b;          // ping-pong [Q_max][d]
+    int fu;
+    int *ub;
+    unsigned *av, *sv;
+    unsigned short *bins;            // [Q_max][S_local]
+    unsigned char *pq;               // [Q_max][NB]
+    unsigned *thr, *nsel;
+    float *zbuf;
+    int smem_optin;
+    // optional timing of k_big_scores (qmann_bigmem_profile_*)
+    bool profile;
+    cudaEvent_t pev[2 * MAXH];
+    unsigned pused;
+    double pms;
+    unsigned pcount;
+};
+
+template <int MODE, int QB>
+static int launch_scores(qmann_bigmem *b, const ScoreParams &sp, cudaStream_t st)
+{
+    const unsigned d = sp.d, warps = 8;
+    const size_t smem = (size_t)QB * d * 4 * (MODE == 3 ? 3 : 1) + (size_t)warps * 32 * (d + 16);
+    if (smem > (size_t)b->smem_optin) return bfail(QMANN_E_NOMEM, "score tile does not fit shared memory");
+    BCUDA(cudaFuncSetAttribute(k_big_scores<MODE, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned long long tiles = (sp.S_local + 31) / 32;
+    const unsigned qblocks = (sp.Q + QB - 1) / QB;
+    unsigned gx = (unsigned)std::min<unsigned long long>((tiles + warps - 1) / warps, (unsigned long long)b->sm_count * 2);
+    gx = std::max(1u, gx);
+    k_big_scores<MODE, QB><<<dim3(gx, qblocks), warps * 32, smem, st>>>(sp);
+    count_launch();
+    BCUDA(cudaPeekAtLastError());
+    return QMANN_OK;
+}
+
+extern "C" {
+
+const char *qmann_bigmem_last_error(void) { return g_berr.c_str(); }
+
+int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann_weights *w, const int8_t *const *dev_M,
+                        const int8_t *const *dev_C, uint64_t S_total, uint64_t slot0, uint64_t S_local, uint32_t Q_max)
+{
+    if (!out || !cfg || !w || !dev_M || !dev_C) return bfail(QMANN_E_ARG, "null argument");
+    *out = nullptr;
+    const qmann_config &c = *cfg;
+    if (c.H == 0 || c.H > MAXH) return bfail(QMANN_E_ARG, "H must be in 1..8");
+    if (c.mode != 2 && c.mode != 3) return bfail(QMANN_E_ARG, "attention mode must be 2 or 3");
+    if (c.d == 0 || c.d % 16 || c.d > 512) return bfail(QMANN_E_ARG, "d must be a multiple of 16 in 16..512");
+    if (Q_max == 0 || Q_max > 65535) return bfail(QMANN_E_ARG, "Q_max must be in 1..65535");
+    if (slot0 + S_local > S_total) return bfail(QMANN_E_ARG, "shard exceeds the memory");
+    auto okfmt = [](unsigned i, unsigned f) { return i + f >= 1 && i + f <= 7; };
+    for (unsigned h = 0; h < c.H; h++)
+        if (!okfmt(c.iwl[h], c.frac[h]) || !okfmt(c.iwl_w[h], c.frac_w[h]) || !okfmt(c.iwl_att[h], c.frac_att[h]))
+            return bfail(QMANN_E_ARG, "formats must satisfy 1 <= iwl+frac <= 7");
+    if (!okfmt(c.iwl_bin, c.frac_bin)) return bfail(QMANN_E_ARG, "bin format must satisfy 1 <= iwl+frac <= 7");
+    if (c.mode == 3 && (c.const_scale > 0 || c.const_scale < -16)) return bfail(QMANN_E_ARG, "const_scale must be in -16..0");
+    for (unsigned h = 0; h < c.H; h++)
+        if ((S_local && (!dev_M[h] || !dev_C[h])) || (c.lin_map && !w->dev_Hm[h])) return bfail(QMANN_E_ARG, "missing per-hop pointer");
+
+    qmann_bigmem *b = new qmann_bigmem();
+    memset(b, 0, sizeof(*b));
+    b->cfg = c;
+    int dev = 0;
+    BCUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    BCUDA(cudaGetDeviceProperties(&prop, dev));
+    b->sm_count = prop.multiProcessorCount;
+    BCUDA(cudaDeviceGetAttribute(&b->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    b->S_total = S_total; b->slot0 = slot0; b->S_local = S_local; b->Q_max = Q_max;
+    unsigned la_max = 0;
+    for (unsigned h = 0; h < c.H; h++) {
+        HopFmt &f = b->f[h];
+        f.fw = c.frac_w[h]; f.lw = fixed_max(c.iwl_w[h], c.frac_w[h]);
+        f.fa = c.frac_att[h]; f.ia = c.iwl_att[h]; f.la = fixed_max(c.iwl_att[h], c.frac_att[h]);
+        f.ff = c.frac[h]; f.iff = c.iwl[h]; f.lf = fixed_max(c.iwl[h], c.frac[h]);
+        f.fb = c.frac_bin; f.lb = fixed_max(c.iwl_bin, c.frac_bin);
+        la_max = std::max(la_max, (unsigned)f.la);
+        b->M[h] = dev_M[h]; b->C[h] = dev_C[h];
+    }
+    b->bias = (c.mode == 3) ? 127u * c.d : la_max;
+    b->NB = 2 * b->bias + 1;
+    if (b->NB > 65536) { delete b; return bfail(QMANN_E_ARG, "score range does not fit 16-bit bins (mode 3 needs d <= 258)"); }
+    b->dev_W = w->dev_W;
+    const size_t Qd = (size_t)Q_max * c.d;
+    BCUDA(cudaMalloc((void **)&b->u_a, Qd));
+    BCUDA(cudaMalloc((void **)&b->u_b, Qd));
+    BCUDA(cudaMalloc((void **)&b->ub, Qd * 4));
+    BCUDA(cudaMalloc((void **)&b->av, Qd * 4));
+    BCUDA(cudaMalloc((void **)&b->sv, Qd * 4));
+    BCUDA(cudaMalloc((void **)&b->bins, std::max<size_t>(2, (size_t)Q_max * S_local * 2)));
+    BCUDA(cudaMalloc((void **)&b->pq, (size_t)Q_max * b->NB));
+    BCUDA(cudaMalloc((void **)&b->thr, (size_t)Q_max * 4));
+    BCUDA(cudaMalloc((void **)&b->nsel, (size_t)Q_max * 4));
+    if (c.V) BCUDA(cudaMalloc((void **)&b->zbuf, (size_t)Q_max * c.V * 4));
+    for (unsigned h = 0; h < c.H; h++) {
+        if (!c.lin_map) continue;
+        BCUDA(cudaMalloc((void **)&b->dev_H[h], (size_t)c.d * c.d));
+        k_big_quant_H<<<64, 256>>>(w->dev_Hm[h], b->dev_H[h], c.d * c.d, c.iwl_w[h], c.frac_w[h]);
+        count_launch();
+    }
+    BCUDA(cudaDeviceSynchronize());
+    *out = b;
+    return QMANN_OK;
+}
+
+void qmann_bigmem_destroy(qmann_bigmem *b)
+{
+    if (!b) return;
+    cudaFree(b->u_a); cudaFree(b->u_b); cudaFree(b->ub); cudaFree(b->av); cudaFree(b->sv); cudaFree(b->bins);
+    cudaFree(b->pq); cudaFree(b->thr); cudaFree(b->nsel); cudaFree(b->zbuf);
+    for (int h = 0; h < MAXH; h++) cudaFree(b->dev_H[h]);
+    if (b->pev[0]) for (int i = 0; i < 2 * MAXH; i++) cudaEventDestroy(b->pev[i]);
+    delete b;
+}
+
+uint32_t qmann_bigmem_num_bins(const qmann_bigmem *b) { return b ? b->NB : 0; }
+
+int qmann_bigmem_begin(qmann_bigmem *b, const int8_t *dev_u0, uint32_t Q, void *stream)
+{
+    if (!b || !dev_u0) return bfail(QMANN_E_ARG, "null argument");
+    if (Q == 0 || Q > b->Q_max) return bfail(QMANN_E_ARG, "Q must be in 1..Q_max");
+    b->Q = Q;
+    b->fu = (int)b->cfg.frac_w[0];        // emb_q outputs in the hop-0 weight format (MemN2N.c:826)
+    BCUDA(cudaMemcpyAsync(b->u_a, dev_u0, (size_t)Q * b->cfg.d, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return QMANN_OK;
+}
+
+int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, void *stream)
+{
+    if (!b || !dev_hist) return bfail(QMANN_E_ARG, "null argument");
+    if (h >= b->cfg.H || b->Q == 0) return bfail(QMANN_E_ARG, "bad hop or no query batch (call qmann_bigmem_begin)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned Q = b->Q, d = b->cfg.d;
+    const HopFmt &f = b->f[h];
+    k_big_prep_query<<<std::min<unsigned>(256, (Q * d + 255) / 256), 256, 0, st>>>(b->u_a, b->fu, Q, d, (int)b->cfg.mode, f, b->ub, b->av, b->sv);
+    count_launch();
+    BCUDA(cudaMemsetAsync(dev_hist, 0, (size_t)Q * b->NB * 4, st));
+    if (b->S_local) {
+        ScoreParams sp;
+        sp.M = b->M[h]; sp.S_local = b->S_local; sp.d = d; sp.Q = Q; sp.f = f; sp.const_scale = b->cfg.const_scale;
+        sp.ub = b->ub; sp.av = b->av; sp.sv = b->sv; sp.bins = b->bins;
+        sp.bias = (b->cfg.mode == 3) ? b->bias : (unsigned)f.la;
+        int rc;
+        const bool prof = b->profile && b->pused + 2 <= 2 * MAXH;
+        if (prof) BCUDA(cudaEventRecord(b->pev[b->pused], st));
+        if (b->cfg.mode == 3) rc = (Q >= 4) ? launch_scores<3, 4>(b, sp, st) : launch_scores<3, 1>(b, sp, st);
+        else rc = (Q >= 16) ? launch_scores<2, 16>(b, sp, st) : (Q >= 4 ? launch_scores<2, 4>(b, sp, st) : launch_scores<2, 1>(b, sp, st));
+        if (rc) return rc;
+        if (prof) { BCUDA(cudaEventRecord(b->pev[b->pused + 1], st)); b->pused += 2; }
+        // mode 2 bins are code + la of THIS hop; the histogram is indexed with the common bias
+        const int use_smem = b->NB <= 8192;
+        const unsigned gx = (unsigned)std::min<unsigned long long>((b->S_local + 255) / 256, (unsigned long long)b->sm_count * 4);
+        k_big_hist<<<dim3(std::max(1u, gx), Q), 256, use_smem ? b->NB * 4 : 0, st>>>(b->bins, b->S_local, b->NB, dev_hist, use_smem);
+        count_launch();
+        BCUDA(cudaPeekAtLastError());
+    }
+    return QMANN_OK;
+}
+
+int qmann_bigmem_hop_read(qmann_bigmem *b, uint32_t h, const uint32_t *dev_hist, int32_t *dev_partial, float *dev_pbin, void *stream)
+{
+    if (!b || !dev_hist || !dev_partial) return bfail(QMANN_E_ARG, "null argument");
+    if (h >= b->cfg.H || b->Q == 0) return bfail(QMANN_E_ARG, "bad hop or no query batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned Q = b->Q, d = b->cfg.d;
+    const HopFmt &f = b->f[h];
+    SoftmaxParams sp;
+    sp.hist = dev_hist; sp.NB = b->NB; sp.bias = (b->cfg.mode == 3) ? b->bias : (unsigned)f.la; sp.mode = (int)b->cfg.mode;
+    sp.fa = f.fa; sp.ia = f.ia; sp.const_scale = b->cfg.const_scale; sp.iff = f.iff; sp.ff = f.ff;
+    sp.pq = b->pq; sp.thr = b->thr; sp.pbin = dev_pbin; sp.total_out = nullptr;
+    k_big_softmax<<<Q, SOFTMAX_RANGES, 0, st>>>(sp);
+    count_launch();
+    BCUDA(cudaMemsetAsync(dev_partial, 0, (size_t)Q * d * 4, st));
+    BCUDA(cudaMemsetAsync(b->nsel, 0, (size_t)Q * 4, st));
+    if (b->S_local) {
+        ReadParams rp;
+        rp.bins = b->bins; rp.pq = b->pq; rp.thr = b->thr; rp.C = b->C[h]; rp.S_local = b->S_local; rp.NB = b->NB; rp.d = d; rp.f = f;
+        rp.partial = dev_partial; rp.nsel = b->nsel;
+        const unsigned gx = (unsigned)std::min<unsigned long long>((b->S_local + 255) / 256, (unsigned long long)b->sm_count * 4);
+        k_big_read<<<dim3(std::max(1u, gx), Q), 256, 0, st>>>(rp);
+        count_launch();
+    }
+    BCUDA(cudaPeekAtLastError());
+    return QMANN_OK;
+}
+
+int qmann_bigmem_hop_update(qmann_bigmem *b, uint32_t h, const int32_t *dev_partial, int8_t *dev_o, int8_t *dev_g, void *stream)
+{
+    if (!b || !dev_partial) return bfail(QMANN_E_ARG, "null argument");
+    if (h >= b->cfg.H || b->Q == 0) return bfail(QMANN_E_ARG, "bad hop or no query batch");
+    UpdateParams up;
+    up.partial = dev_partial; up.u_in = b->u_a; up.u_out = b->u_b; up.ub = b->ub; up.Hq = b->cfg.lin_map ? b->dev_H[h] : nullptr;
+    up.d = b->cfg.d; up.fu = b->fu; up.f = b->f[h]; up.dbg_o = dev_o; up.dbg_g = dev_g;
+    k_big_update<<<b->Q, 256, 0, (cudaStream_t)stream>>>(up);
+    count_launch();
+    BCUDA(cudaPeekAtLastError());
+    std::swap(b->u_a, b->u_b);
+    b->fu = b->f[h].ff;
+    return QMANN_OK;
+}
+
+int qmann_bigmem_state(qmann_bigmem *b, int8_t *dev_u, int32_t *frac_bits, void *stream)
+{
+    if (!b) return bfail(QMANN_E_ARG, "null argument");
+    if (dev_u && b->Q) BCUDA(cudaMemcpyAsync(dev_u, b->u_a, (size_t)b->Q * b->cfg.d, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (frac_bits) *frac_bits = b->fu;
+    return QMANN_OK;
+}
+
+int qmann_bigmem_profile_enable(qmann_bigmem *b, int enable)
+{
+    if (!b) return bfail(QMANN_E_ARG, "null argument");
+    if (enable && !b->pev[0])
+        for (int i = 0; i < 2 * MAXH; i++) BCUDA(cudaEventCreate(&b->pev[i]));
+    b->profile = enable != 0;
+    b->pused = 0; b->pms = 0.0; b->pcount = 0;
+    return QMANN_OK;
+}
+
+// Folds the pending event pairs (call after the forward has been enqueued; synchronises on them) and returns
+// the accumulated k_big_scores time and launch count since the last reset.
+int qmann_bigmem_profile_read(qmann_bigmem *b, float *ms_scores, uint32_t *n_launches, int reset)
+{
+    if (!b) return bfail(QMANN_E_ARG, "null argument");
+    for (unsigned i = 0; i + 2 <= b->pused; i += 2) {
+        float ms = 0.f;
+        BCUDA(cudaEventSynchronize(b->pev[i + 1]));
+        BCUDA(cudaEventElapsedTime(&ms, b->pev[i], b->pev[i + 1]));
+        b->pms += ms; b->pcount++;
+    }
+    b->pused = 0;
+    if (ms_scores) *ms_scores = (float)b->pms;
+    if (n_launches) *n_launches = b->pcount;
+    if (reset) { b->pms = 0.0; b->pcount = 0; }
+    return QMANN_OK;
+}
+
+int qmann_bigmem_finish(qmann_bigmem *b, uint32_t *dev_pred, float *dev_z, float *dev_h, void *stream)
+{
+    if (!b) return bfail(QMANN_E_ARG, "null argument");
+    if (b->Q == 0) return bfail(QMANN_E_ARG, "no query batch");
+    if (!b->dev_W || !b->cfg.V) return bfail(QMANN_E_ARG, "the memory was created without an answer projection (dev_W, V)");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *z = dev_z ? dev_z : b->zbuf;
+    k_big_answer<<<(b->Q * 32 + 127) / 128, 128, 0, st>>>(b->dev_W, b->u_a, b->fu, b->Q, b->cfg.V, b->cfg.d, z, dev_pred, dev_h);
+    count_launch();
+    BCUDA(cudaPeekAtLastError());
+    return QMANN_OK;
+}
+
+}  // extern "C"

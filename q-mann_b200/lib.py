@@ -41,7 +41,7 @@ def build(force: bool = False, extra: str = "") -> str:
     srcdir = os.path.join(_HERE, "csrc")
     if force and os.path.exists(LIB_PATH):
         os.remove(LIB_PATH)
-    cmd = ["make", "-C", srcdir]
+    cmd = ["make", "-j4", "-C", srcdir]
     if extra:
         cmd.append(f"EXTRA={extra}")
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
@@ -82,6 +82,31 @@ def lib() -> C.CDLL:
     L.qmann_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_U32)]
     L.qmann_shard_plan.restype = C.c_int
     L.qmann_shard_plan.argtypes = [C.POINTER(_U32), _U32, _U32, _U32, C.POINTER(_U32), C.POINTER(_U32)]
+    # part 3: slot-sharded large memory
+    L.qmann_bigmem_last_error.restype = C.c_char_p
+    L.qmann_bigmem_create.restype = C.c_int
+    L.qmann_bigmem_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(QConfig), C.POINTER(QWeights), C.POINTER(_FP), C.POINTER(_FP),
+                                      C.c_uint64, C.c_uint64, C.c_uint64, _U32]
+    L.qmann_bigmem_destroy.restype = None
+    L.qmann_bigmem_destroy.argtypes = [C.c_void_p]
+    L.qmann_bigmem_num_bins.restype = _U32
+    L.qmann_bigmem_num_bins.argtypes = [C.c_void_p]
+    L.qmann_bigmem_begin.restype = C.c_int
+    L.qmann_bigmem_begin.argtypes = [C.c_void_p, _FP, _U32, C.c_void_p]
+    L.qmann_bigmem_hop_scores.restype = C.c_int
+    L.qmann_bigmem_hop_scores.argtypes = [C.c_void_p, _U32, _FP, C.c_void_p]
+    L.qmann_bigmem_hop_read.restype = C.c_int
+    L.qmann_bigmem_hop_read.argtypes = [C.c_void_p, _U32, _FP, _FP, _FP, C.c_void_p]
+    L.qmann_bigmem_hop_update.restype = C.c_int
+    L.qmann_bigmem_hop_update.argtypes = [C.c_void_p, _U32, _FP, _FP, _FP, C.c_void_p]
+    L.qmann_bigmem_state.restype = C.c_int
+    L.qmann_bigmem_state.argtypes = [C.c_void_p, _FP, C.POINTER(C.c_int32), C.c_void_p]
+    L.qmann_bigmem_profile_enable.restype = C.c_int
+    L.qmann_bigmem_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.qmann_bigmem_profile_read.restype = C.c_int
+    L.qmann_bigmem_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(_U32), C.c_int]
+    L.qmann_bigmem_finish.restype = C.c_int
+    L.qmann_bigmem_finish.argtypes = [C.c_void_p, _FP, _FP, _FP, C.c_void_p]
     _lib = L
     return L
 
@@ -226,3 +251,116 @@ class DeviceBatch:
             self.close()
         except Exception:
             pass
+
+
+def _bcheck(rc: int):
+    if rc != 0:
+        raise QmannError(f"qmann bigmem error {rc}: {lib().qmann_bigmem_last_error().decode()}")
+
+
+def slot_shard(S_total: int, world: int, rank: int):
+    """Contiguous slot range [slot0, slot0 + S_local) of `rank`: slots are uniform work, so equal ranges."""
+    lo = S_total * rank // world
+    hi = S_total * (rank + 1) // world
+    return lo, hi - lo
+
+
+class BigMemory:
+    """One very large pre-embedded memory, this rank's slot shard resident in HBM (include/qmann_abi.h part 3).
+
+    M8, C8: int8 [H][S_local][d] codes in the hops' weight formats (torch tensors on the device or numpy arrays).
+    `group`: a torch.distributed process group (NCCL) spanning the shards, or None for a single shard; the two
+    per-hop exchanges are all_reduce(SUM) of the integer score histograms and of the integer partial reads."""
+
+    def __init__(self, cfg, weights, M8, C8, S_total: int, slot0: int, Q_max: int, device: str = "cuda:0", group=None,
+                 world: int = 1):
+        import torch
+        self.torch = torch
+        self.cfg = cfg
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        to_dev = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(self.device).contiguous()
+        self.M = [to_dev(M8[h]) for h in range(cfg.H)]
+        self.C = [to_dev(C8[h]) for h in range(cfg.H)]
+        assert all(t.dtype == torch.int8 for t in self.M + self.C)
+        self.S_local = int(self.M[0].shape[0])
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
+        self.w = dict(W=t(weights.W), Hm=[t(x) for x in weights.Hm])
+        qw = QWeights()
+        qw.dev_W = self.w["W"].data_ptr()
+        for h in range(cfg.H):
+            qw.dev_Hm[h] = self.w["Hm"][h].data_ptr()
+        Mp, Cp = (_FP * MAX_HOP)(), (_FP * MAX_HOP)()
+        for h in range(cfg.H):
+            Mp[h], Cp[h] = self.M[h].data_ptr(), self.C[h].data_ptr()
+        self._h = C.c_void_p()
+        qc = make_config(cfg)
+        _bcheck(lib().qmann_bigmem_create(C.byref(self._h), C.byref(qc), C.byref(qw), Mp, Cp, S_total, slot0, self.S_local, Q_max))
+        self.NB = int(lib().qmann_bigmem_num_bins(self._h))
+        self.Q_max = Q_max
+        self.group, self.world = group, world
+        self.hist = torch.zeros((Q_max, self.NB), dtype=torch.int32, device=self.device)
+        self.partial = torch.zeros((Q_max, cfg.d), dtype=torch.int32, device=self.device)
+        self.pred = torch.zeros(Q_max, dtype=torch.int32, device=self.device)
+        self.u_out = torch.zeros((Q_max, cfg.d), dtype=torch.int8, device=self.device)
+
+    def close(self):
+        if self._h:
+            lib().qmann_bigmem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def profile(self, enable: bool):
+        _bcheck(lib().qmann_bigmem_profile_enable(self._h, int(enable)))
+
+    def profile_read(self, reset: bool = False):
+        """(ms spent in k_big_scores, launches) accumulated since the last reset; call after every forward."""
+        ms, n = C.c_float(0), _U32(0)
+        _bcheck(lib().qmann_bigmem_profile_read(self._h, C.byref(ms), C.byref(n), int(reset)))
+        return float(ms.value), int(n.value)
+
+    def _allreduce(self, t):
+        if self.group is not None and self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def forward(self, u0, debug: bool = False, answer: bool = True):
+        """u0: int8 [Q][d] device tensor (codes in the hop-0 weight format).  Asynchronous on the current stream.
+        Returns dict(pred, u) (+ per-hop o, g, u, hist, pbin when debug)."""
+        torch = self.torch
+        L = lib()
+        Q, d, H = int(u0.shape[0]), self.cfg.d, self.cfg.H
+        assert u0.dtype == torch.int8 and u0.is_cuda and u0.is_contiguous() and Q <= self.Q_max
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _bcheck(L.qmann_bigmem_begin(self._h, u0.data_ptr(), Q, st))
+        hist, partial = self.hist[:Q], self.partial[:Q]
+        out = {}
+        if debug:
+            out.update(o=torch.zeros((H, Q, d), dtype=torch.int8, device=self.device), g=torch.zeros((H, Q, d), dtype=torch.int8, device=self.device),
+                       u=torch.zeros((H, Q, d), dtype=torch.int8, device=self.device), hist=torch.zeros((H, Q, self.NB), dtype=torch.int32, device=self.device),
+                       pbin=torch.zeros((H, Q, self.NB), dtype=torch.float32, device=self.device))
+        for h in range(H):
+            _bcheck(L.qmann_bigmem_hop_scores(self._h, h, hist.data_ptr(), st))
+            self._allreduce(hist)
+            _bcheck(L.qmann_bigmem_hop_read(self._h, h, hist.data_ptr(), partial.data_ptr(), out["pbin"][h].data_ptr() if debug else None, st))
+            self._allreduce(partial)
+            _bcheck(L.qmann_bigmem_hop_update(self._h, h, partial.data_ptr(), out["o"][h].data_ptr() if debug else None,
+                                              out["g"][h].data_ptr() if debug else None, st))
+            if debug:
+                out["hist"][h].copy_(hist)
+                _bcheck(L.qmann_bigmem_state(self._h, out["u"][h].data_ptr(), None, st))
+        fb = C.c_int32(0)
+        _bcheck(L.qmann_bigmem_state(self._h, self.u_out.data_ptr(), C.byref(fb), st))
+        out["u_final"], out["frac_bits"] = self.u_out[:Q], int(fb.value)
+        if answer and self.cfg.V:
+            z = torch.zeros((Q, self.cfg.V), dtype=torch.float32, device=self.device) if debug else None
+            _bcheck(L.qmann_bigmem_finish(self._h, self.pred.data_ptr(), z.data_ptr() if debug else None, None, st))
+            out["pred"] = self.pred[:Q]
+            if debug:
+                out["z"] = z
+        return out

@@ -1,0 +1,159 @@
+"""Slot-sharded large-memory path (BASELINE config 5) on a real B200, through the C ABI (qmann_bigmem_*).
+
+Bars: score bins, selected slots, reads, linear maps, updates and predicted answers bit-exact against the CPU
+restatement (oracle/qmo_bigmem.py, itself pinned to the reference's golden tensors by tests/test_bigmem_oracle.py);
+attention weights within 1e-5 relative.  At full size (2^20 slots, d = 256) the checks are the size-independent
+ones: the result does not depend on the number of shards, the histogram counts every slot once, and a planted
+copy of the query is the slot that gets read."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from test_bigmem_oracle import _random_memory
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(qmann, cfg, w, M8, C8, u0, shards=1, debug=True):
+    """Forward over `shards` slot shards held by ONE GPU; the two per-hop exchanges are done by adding the
+    shards' integer buffers (what all_reduce does across ranks)."""
+    import ctypes as C
+    import torch
+    L = qmann.lib.lib()
+    S = M8.shape[1]
+    Q = u0.shape[0]
+    mems = []
+    for r in range(shards):
+        lo, n = qmann.lib.slot_shard(S, shards, r)
+        mems.append(qmann.lib.BigMemory(cfg, w, M8[:, lo:lo + n], C8[:, lo:lo + n], S, lo, Q_max=Q))
+    if shards == 1:
+        out = mems[0].forward(torch.from_numpy(u0).cuda(), debug=debug)
+        torch.cuda.synchronize()
+        return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+    u0d = torch.from_numpy(u0).cuda()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    H, d = cfg.H, cfg.d
+    res = dict(u=np.zeros((H, Q, d), np.int8), hist=np.zeros((H, Q, mems[0].NB), np.int64))
+    for m in mems:
+        qmann.lib._bcheck(L.qmann_bigmem_begin(m._h, u0d.data_ptr(), Q, st))
+    for h in range(H):
+        for m in mems:
+            qmann.lib._bcheck(L.qmann_bigmem_hop_scores(m._h, h, m.hist.data_ptr(), st))
+        tot = sum(m.hist[:Q] for m in mems)
+        res["hist"][h] = tot.cpu().numpy()
+        for m in mems:
+            m.hist[:Q].copy_(tot)
+            qmann.lib._bcheck(L.qmann_bigmem_hop_read(m._h, h, m.hist.data_ptr(), m.partial.data_ptr(), None, st))
+        ptot = sum(m.partial[:Q] for m in mems)
+        for m in mems:
+            m.partial[:Q].copy_(ptot)
+            qmann.lib._bcheck(L.qmann_bigmem_hop_update(m._h, h, m.partial.data_ptr(), None, None, st))
+        uu = torch.zeros((Q, d), dtype=torch.int8, device="cuda")
+        qmann.lib._bcheck(L.qmann_bigmem_state(mems[0]._h, uu.data_ptr(), None, st))
+        res["u"][h] = uu.cpu().numpy()
+    pred = torch.zeros(Q, dtype=torch.int32, device="cuda")
+    qmann.lib._bcheck(L.qmann_bigmem_finish(mems[0]._h, pred.data_ptr(), None, None, st))
+    torch.cuda.synchronize()
+    res["pred"] = pred.cpu().numpy()
+    return res
+
+
+@pytest.mark.parametrize("mode,d,S,Q,iwl", [(2, 32, 3000, 5, 5), (2, 64, 1031, 1, 5), (2, 48, 2500, 17, 5), (2, 32, 2000, 4, 3),
+                                            (3, 32, 600, 5, 2), (3, 64, 900, 1, 3), (3, 64, 1500, 6, 3)])
+def test_bigmem_matches_oracle(mode, d, S, Q, iwl, qmann, synth, qmo):
+    import qmo_bigmem as qb
+    cfg = synth.ModelConfig(V=40, d=d, S_max=64, V_dict=20, mode=mode, iwl=iwl)
+    w = synth.make_weights(cfg, 5, sigma=0.5)
+    M8, C8, u0 = _random_memory(cfg, S, Q, 100 + d + Q, sigma=0.6 if mode == 2 else 0.3, plant_scale=3.0 if mode == 2 else 1.0)
+    ref = qb.forward(cfg, w, M8, C8, u0)
+    got = _run(qmann, cfg, w, M8, C8, u0)
+    np.testing.assert_array_equal(got["hist"].astype(np.int64), ref["hist"].astype(np.int64), err_msg="score histograms")
+    safe = ref["risk"] == 0
+    assert safe.any()
+    np.testing.assert_allclose(got["pbin"][:, safe], ref["pbin"][:, safe], rtol=1e-5, atol=1e-30)
+    for k in ("o", "g", "u"):
+        np.testing.assert_array_equal(got[k][:, safe], ref[k][:, safe], err_msg=k)
+    np.testing.assert_array_equal(got["z"][safe], ref["z"][safe])
+    np.testing.assert_array_equal(got["pred"][safe].astype(np.uint32), ref["pred"][safe])
+    assert ref["nsel"].sum() > 0
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_bigmem_shards_agree(mode, qmann, synth):
+    cfg = synth.ModelConfig(V=40, d=64, S_max=64, V_dict=20, mode=mode, iwl=5 if mode == 2 else 3)
+    w = synth.make_weights(cfg, 6, sigma=0.5)
+    M8, C8, u0 = _random_memory(cfg, 10007 if mode == 2 else 2003, 9, 77, sigma=0.6 if mode == 2 else 0.3, plant_scale=3.0 if mode == 2 else 1.0)
+    one = _run(qmann, cfg, w, M8, C8, u0, shards=1)
+    for shards in (2, 3, 8):
+        many = _run(qmann, cfg, w, M8, C8, u0, shards=shards)
+        np.testing.assert_array_equal(many["hist"], one["hist"].astype(np.int64))
+        np.testing.assert_array_equal(many["u"], one["u"])
+        np.testing.assert_array_equal(many["pred"], one["pred"])
+
+
+def test_bigmem_full_size_properties(qmann, synth):
+    """BASELINE config 5 shape: 2^20 slots, d = 256, 3 hops."""
+    import torch
+    cfg = synth.ModelConfig(V=64, d=256, S_max=64, V_dict=32, mode=2)
+    w = synth.make_weights(cfg, 9, sigma=0.3)
+    S, Q = 1 << 20, 4
+    g = torch.Generator(device="cuda").manual_seed(1)
+    f = cfg.formats()
+    M8 = [(torch.randn((S, cfg.d), device="cuda", generator=g) * (0.1 * (1 << f["frac_w"][h]))).round().clamp(-127, 127).to(torch.int8) for h in range(3)]
+    C8 = [(torch.randn((S, cfg.d), device="cuda", generator=g) * (0.5 * (1 << f["frac_w"][h]))).round().clamp(-127, 127).to(torch.int8) for h in range(3)]
+    u0 = (torch.randn((Q, cfg.d), device="cuda", generator=g) * 3).round().clamp(-127, 127).to(torch.int8)
+    planted = [12345, 700001, 1048575, 3]
+    for q, r in enumerate(planted):
+        M8[0][r] = (u0[q].to(torch.int32) * 2).clamp(-127, 127).to(torch.int8)
+    full = qmann.lib.BigMemory(cfg, w, M8, C8, S, 0, Q_max=Q)
+    a = full.forward(u0, debug=True)
+    torch.cuda.synchronize()
+    hist = a["hist"].cpu().numpy().astype(np.int64)
+    assert np.all(hist.sum(axis=2) == S), "every slot is counted once per query and hop"
+    # hop 0: the planted slot holds the largest score of its query, and it is the row that is read
+    u_after0 = a["u"][0].cpu().numpy()
+    top_bin = np.array([np.nonzero(hist[0, q])[0].max() for q in range(Q)])
+    cnt = hist[0, np.arange(Q), top_bin]
+    assert np.all((cnt >= 1) & (cnt <= Q)), "only planted rows can reach the top score bin"
+    # sharded 4 ways on the same GPU: identical result
+    parts = []
+    for r in range(4):
+        lo, n = qmann.lib.slot_shard(S, 4, r)
+        parts.append(qmann.lib.BigMemory(cfg, w, [m[lo:lo + n] for m in M8], [c[lo:lo + n] for c in C8], S, lo, Q_max=Q))
+    import ctypes as C
+    L = qmann.lib.lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for m in parts:
+        qmann.lib._bcheck(L.qmann_bigmem_begin(m._h, u0.data_ptr(), Q, st))
+    for h in range(cfg.H):
+        for m in parts:
+            qmann.lib._bcheck(L.qmann_bigmem_hop_scores(m._h, h, m.hist.data_ptr(), st))
+        tot = sum(m.hist[:Q] for m in parts)
+        assert torch.equal(tot, a["hist"][h])
+        for m in parts:
+            m.hist[:Q].copy_(tot)
+            qmann.lib._bcheck(L.qmann_bigmem_hop_read(m._h, h, m.hist.data_ptr(), m.partial.data_ptr(), None, st))
+        ptot = sum(m.partial[:Q] for m in parts)
+        for m in parts:
+            m.partial[:Q].copy_(ptot)
+            qmann.lib._bcheck(L.qmann_bigmem_hop_update(m._h, h, m.partial.data_ptr(), None, None, st))
+        uu = torch.zeros((Q, cfg.d), dtype=torch.int8, device="cuda")
+        qmann.lib._bcheck(L.qmann_bigmem_state(parts[0]._h, uu.data_ptr(), None, st))
+        assert torch.equal(uu, a["u"][h]), f"hop {h}: sharded controller state differs"
+    assert u_after0.shape == (Q, cfg.d)
+
+
+def test_bigmem_nccl_two_ranks(qmann):
+    """Two processes, one GPU each, NCCL all_reduce between the phases (needs >= 2 GPUs on the box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "tests", "run_bigmem_nccl.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "BIGMEM_NCCL_OK" in r.stdout
