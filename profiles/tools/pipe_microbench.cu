@@ -55,6 +55,58 @@ __global__ void __launch_bounds__(1024, 1) k(unsigned *out, unsigned long long *
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+#define EMIT(OPX, i)                                                                                            \
+    if (OPX == IMAD) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(c));                      \
+    if (OPX == IDP4A) asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(r[i]) : "r"(b), "r"(c));                   \
+    if (OPX == VIADD2) r[i] = __vadd2(r[i], b);                                                                     \
+    if (OPX == VIADDMNMX) r[i] = __viaddmin_s32_relu((int)r[i], (int)b, (int)c);                                    \
+    if (OPX == LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[i]) : "r"(b), "r"(c));                  \
+    if (OPX == SHFR) asm volatile("shr.s32 %0, %0, %1;" : "+r"(r[i]) : "r"(sh));                                    \
+    if (OPX == PRMT) asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(c & 0x7777u));              \
+    if (OPX == HFMA2) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(c));                   \
+    if (OPX == HMNMX2) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(r[i]) : "r"(b));                                 \
+    if (OPX == FFMARZ) asm volatile("fma.rz.f32 %0, %0, %1, %2;" : "+f"(*(float *)&r[i]) : "f"(__uint_as_float(b)), "f"(__uint_as_float(c))); \
+    if (OPX == IADD3) asm volatile("add.s32 %0, %0, %1;" : "+r"(r[i]) : "r"(b));                                    \
+    if (OPX == FMNMX) asm volatile("min.f32 %0, %0, %1;" : "+f"(*(float *)&r[i]) : "f"(__uint_as_float(b)));       \
+    if (OPX == FADD) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(*(float *)&r[i]) : "f"(__uint_as_float(b)));     \
+    if (OPX == VIMNMX2) r[i] = __vmaxs2(r[i], b);                                                                   \
+    if (OPX == I2FP) { float f; asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(r[i])); r[i] = __float_as_uint(f); }
+
+template <int A, int B>
+__global__ void __launch_bounds__(1024, 1) kpair(unsigned *out, unsigned long long *cyc, int iters, unsigned seed, unsigned sh)
+{
+    unsigned r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = seed * (i + 1) + threadIdx.x;
+    unsigned b = seed | 1u, c = seed ^ 0x1234u;
+    const unsigned long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+        EMIT(A, 0) EMIT(B, 1) EMIT(A, 2) EMIT(B, 3) EMIT(A, 4) EMIT(B, 5) EMIT(A, 6) EMIT(B, 7)
+    }
+    const unsigned long long t1 = clock64();
+    unsigned acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc ^= r[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int A, int B>
+void runpair(unsigned *out, unsigned long long *cyc, int sms)
+{
+    const int iters = 4096;
+    kpair<A, B><<<sms, 1024>>>(out, cyc, iters, 12345u, 1u);
+    kpair<A, B><<<sms, 1024>>>(out, cyc, iters, 12345u, 1u);
+    cudaDeviceSynchronize();
+    unsigned long long h[256];
+    cudaMemcpy(h, cyc, sms * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < sms; i++) avg += (double)h[i];
+    avg /= sms;
+    const double winst = 32.0 * iters * 8;
+    printf("%-22s + %-22s %7.3f warp-inst/clk/SM\n", names[A], names[B], winst / avg);
+}
+
 template <int OP>
 void run(unsigned *out, unsigned long long *cyc, int sms)
 {
@@ -86,5 +138,13 @@ int main()
     run<PRMT>(out, cyc, sms); run<HFMA2>(out, cyc, sms); run<HMNMX2>(out, cyc, sms); run<HADD2F32>(out, cyc, sms);
     run<FFMARZ>(out, cyc, sms); run<I2FP>(out, cyc, sms); run<IADD3>(out, cyc, sms); run<FMNMX>(out, cyc, sms);
     run<FADD>(out, cyc, sms); run<VIMNMX2>(out, cyc, sms); run<MIX_ALU_FMA>(out, cyc, sms); run<LDS32>(out, cyc, sms); run<LDS128>(out, cyc, sms);
+    printf("pairs (4+4 alternating independent chains): ~3.7 = different pipes, ~2 = same half-rate pipe\n");
+    runpair<SHFR, SHFR>(out, cyc, sms); runpair<IMAD, SHFR>(out, cyc, sms); runpair<LOP3, SHFR>(out, cyc, sms); runpair<IMAD, VIADDMNMX>(out, cyc, sms);
+    runpair<LOP3, VIADDMNMX>(out, cyc, sms); runpair<IMAD, IDP4A>(out, cyc, sms); runpair<LOP3, IDP4A>(out, cyc, sms); runpair<IADD3, IMAD>(out, cyc, sms);
+    runpair<IADD3, LOP3>(out, cyc, sms); runpair<FMNMX, LOP3>(out, cyc, sms); runpair<FMNMX, IMAD>(out, cyc, sms); runpair<FADD, IMAD>(out, cyc, sms);
+    runpair<FADD, LOP3>(out, cyc, sms); runpair<VIMNMX2, LOP3>(out, cyc, sms); runpair<VIMNMX2, IMAD>(out, cyc, sms); runpair<HFMA2, IMAD>(out, cyc, sms);
+    runpair<HFMA2, LOP3>(out, cyc, sms); runpair<PRMT, IMAD>(out, cyc, sms); runpair<VIADD2, IMAD>(out, cyc, sms); runpair<I2FP, IMAD>(out, cyc, sms);
+    runpair<I2FP, LOP3>(out, cyc, sms); runpair<FFMARZ, IMAD>(out, cyc, sms); runpair<FFMARZ, FADD>(out, cyc, sms); runpair<IADD3, FADD>(out, cyc, sms);
+    runpair<IADD3, VIMNMX2>(out, cyc, sms); runpair<HMNMX2, LOP3>(out, cyc, sms); runpair<HMNMX2, IMAD>(out, cyc, sms);
     return 0;
 }

@@ -285,30 +285,81 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
             __syncwarp();
 
             // ---- linear map (MemN2N.c:873, layer_cuda.cu:49-68) and update (MemN2N.c:889, layer_cuda.cu:1535) ----
-            const int lw2 = 2 * lw;
+            if (p.lin_map && p.lut) {
+                // g[i] = Q_w(sum_j T[j][Q_bin(u[j])][i]): every product Q_w(Q_w(Hm[i][j]) * Q_bin(u[j])) is a function of
+                // one 8-bit activation, so the d*d quantised products become a gather-and-sum of d table rows
+                int gacc[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) gacc[k] = 0;
+                const signed char *lut = p.lut + p.offL[h] + 16u * q;
 #pragma unroll 1
-            for (unsigned i0 = 0; i0 < d; i0 += 32) {
-                const unsigned i = i0 + lane;
-                int a_f = 0;
-                if (p.lin_map) {
-                    const unsigned hrow = p.offH[h] + min(i, d - 1) * p.HS;
-                    int s_ = 0;
-                    const unsigned d4 = (d + 3) / 4;
-#pragma unroll 2
-                    for (unsigned j4 = 0; j4 < d4; j4++) {
-                        const unsigned hw = *reinterpret_cast<const unsigned *>(smem + hrow + 4u * j4);
-                        const int4 uu = *reinterpret_cast<const int4 *>(ub32 + 4 * j4);
-                        s_ += clamp_biased(shr0m(sbyte_prmt<0>(hw) * uu.x, fb, mb), lw, lw2);
-                        s_ += clamp_biased(shr0m(sbyte_prmt<1>(hw) * uu.y, fb, mb), lw, lw2);
-                        s_ += clamp_biased(shr0m(sbyte_prmt<2>(hw) * uu.z, fb, mb), lw, lw2);
-                        s_ += clamp_biased(shr0m(((int)hw >> 24) * uu.w, fb, mb), lw, lw2);
+                for (unsigned jb = 0; jb < d; jb += 8 * G) {
+                    // eight independent 128-bit gathers (L2-resident table) in flight per lane before the first use
+                    uint4 t[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const unsigned j = jb + (unsigned)i * G + g;
+                        t[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (j < d) t[i] = __ldg(reinterpret_cast<const uint4 *>(lut + (size_t)(j * 255u + (unsigned)(ub32[j] + 127)) * DP));
                     }
-                    a_f = qi_requant(qi_clamp(s_ - (int)(4u * d4) * lw, lw), fw, lf, ff);
-                } else if (i < d) {
-                    a_f = qi_requant((int)uvec[i], fu, lf, ff);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        gacc[0] = __dp4a((int)t[i].x, sel[0], gacc[0]);   gacc[1] = __dp4a((int)t[i].x, sel[1], gacc[1]);
+                        gacc[2] = __dp4a((int)t[i].x, sel[2], gacc[2]);   gacc[3] = __dp4a((int)t[i].x, sel[3], gacc[3]);
+                        gacc[4] = __dp4a((int)t[i].y, sel[0], gacc[4]);   gacc[5] = __dp4a((int)t[i].y, sel[1], gacc[5]);
+                        gacc[6] = __dp4a((int)t[i].y, sel[2], gacc[6]);   gacc[7] = __dp4a((int)t[i].y, sel[3], gacc[7]);
+                        gacc[8] = __dp4a((int)t[i].z, sel[0], gacc[8]);   gacc[9] = __dp4a((int)t[i].z, sel[1], gacc[9]);
+                        gacc[10] = __dp4a((int)t[i].z, sel[2], gacc[10]); gacc[11] = __dp4a((int)t[i].z, sel[3], gacc[11]);
+                        gacc[12] = __dp4a((int)t[i].w, sel[0], gacc[12]); gacc[13] = __dp4a((int)t[i].w, sel[1], gacc[13]);
+                        gacc[14] = __dp4a((int)t[i].w, sel[2], gacc[14]); gacc[15] = __dp4a((int)t[i].w, sel[3], gacc[15]);
+                    }
                 }
-                __syncwarp();
-                if (i < d) uvec[i] = (signed char)qi_clamp(a_f + (int)ovec[i], lf);
+#pragma unroll
+                for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+                    for (int k = 0; k < 16; k++) gacc[k] += __shfl_xor_sync(0xffffffffu, gacc[k], o);
+                if (g == 0) {
+                    const uint4 o4 = *reinterpret_cast<const uint4 *>(ovec + 16 * q);
+                    const unsigned ow[4] = {o4.x, o4.y, o4.z, o4.w};
+                    unsigned packed[4];
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; w4++) {
+                        unsigned v = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int a_f = qi_requant(qi_clamp(gacc[4 * w4 + b], lw), fw, lf, ff);
+                            v |= ((unsigned)(qi_clamp(a_f + sbyte(ow[w4], b), lf) & 0xFF)) << (8 * b);
+                        }
+                        packed[w4] = v;
+                    }
+                    *reinterpret_cast<uint4 *>(uvec + 16 * q) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+            } else {
+                const int lw2 = 2 * lw;
+#pragma unroll 1
+                for (unsigned i0 = 0; i0 < d; i0 += 32) {
+                    const unsigned i = i0 + lane;
+                    int a_f = 0;
+                    if (p.lin_map) {
+                        const unsigned hrow = p.offH[h] + min(i, d - 1) * p.HS;
+                        int s_ = 0;
+                        const unsigned d4 = (d + 3) / 4;
+#pragma unroll 2
+                        for (unsigned j4 = 0; j4 < d4; j4++) {
+                            const unsigned hw = *reinterpret_cast<const unsigned *>(smem + hrow + 4u * j4);
+                            const int4 uu = *reinterpret_cast<const int4 *>(ub32 + 4 * j4);
+                            s_ += clamp_biased(shr0m(sbyte_prmt<0>(hw) * uu.x, fb, mb), lw, lw2);
+                            s_ += clamp_biased(shr0m(sbyte_prmt<1>(hw) * uu.y, fb, mb), lw, lw2);
+                            s_ += clamp_biased(shr0m(sbyte_prmt<2>(hw) * uu.z, fb, mb), lw, lw2);
+                            s_ += clamp_biased(shr0m(((int)hw >> 24) * uu.w, fb, mb), lw, lw2);
+                        }
+                        a_f = qi_requant(qi_clamp(s_ - (int)(4u * d4) * lw, lw), fw, lf, ff);
+                    } else if (i < d) {
+                        a_f = qi_requant((int)uvec[i], fu, lf, ff);
+                    }
+                    __syncwarp();
+                    if (i < d) uvec[i] = (signed char)qi_clamp(a_f + (int)ovec[i], lf);
+                }
             }
             fu = ff;
             __syncwarp();

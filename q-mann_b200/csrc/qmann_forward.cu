@@ -68,6 +68,7 @@ struct qmann_model {
     int device;
     int sm_count;
     unsigned char *dev_img;
+    signed char *dev_lut = nullptr;          // linear-map product tables (k_prep_lut), NULL when too large
     FwdParams base;                // everything but the per-call fields
     unsigned LPR, NW, smem_bytes;
     unsigned rec_stride, off_rend, off_exc, off_ent, lcap;
@@ -289,6 +290,16 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
             count_launch();
         }
     }
+    // linear-map product tables: H * d * 255 rows of DP bytes (2.4 MB at d = 50); skipped beyond 64 MB
+    if (c.lin_map && (size_t)c.H * c.d * 255 * DP <= (64u << 20)) {
+        QCUDA(cudaMalloc((void **)&m->dev_lut, (size_t)c.H * c.d * 255 * DP));
+        for (unsigned h = 0; h < c.H; h++) {
+            p.offL[h] = (unsigned)((size_t)h * c.d * 255 * DP);
+            k_prep_lut<<<256, 256>>>(w->dev_Hm[h], m->dev_lut + p.offL[h], c.d, DP, c.iwl_w[h], c.frac_w[h], c.frac_bin);
+            count_launch();
+        }
+        p.lut = m->dev_lut;
+    }
     k_prep_ans<<<64, 256>>>(w->dev_W, reinterpret_cast<float *>(m->dev_img + p.offW), c.V, c.d, WS);
     count_launch();
     // count splitting (k_compact): per-column max |code| and the largest count every weight format represents
@@ -340,7 +351,7 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
 void qmann_model_destroy(qmann_model *m)
 {
     if (!m) return;
-    cudaFree(m->dev_img); cudaFree(m->dev_rec); cudaFree(m->dev_heap); cudaFree(m->dev_heap_used);
+    cudaFree(m->dev_img); cudaFree(m->dev_lut); cudaFree(m->dev_rec); cudaFree(m->dev_heap); cudaFree(m->dev_heap_used);
     cudaFree(m->dev_slow_list); cudaFree(m->dev_err); cudaFree(m->dev_colmax);
     cudaFree(m->e2e_m); cudaFree(m->e2e_q); cudaFree(m->e2e_a); cudaFree(m->e2e_h); cudaFree(m->e2e_pred); cudaFree(m->e2e_match);
     if (m->e2e_compute) cudaStreamDestroy(m->e2e_compute);

@@ -72,6 +72,10 @@ struct FwdParams {
     // slow_list; the general kernel then takes its work from work_list[0 .. *work_count)
     unsigned *slow_list, *slow_count;
     const unsigned *work_list, *work_count;
+    // linear-map product table (global, L2-resident): lut[offL[h] + (j*255 + v + 127)*DP + i] =
+    // Q_w(Q_w(Hm[i][j]) * v) for every code v of Q_bin(u[j]); NULL: compute the products (large d)
+    const signed char *lut;
+    unsigned offL[MAXH];
     qmann_debug dbg;
 };
 
@@ -96,6 +100,19 @@ __global__ void k_prep_lin(const float *__restrict__ w, signed char *__restrict_
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const unsigned r = (unsigned)(i / HS), c = (unsigned)(i % HS);
         img[i] = (c < d) ? (signed char)qi_encode(w[(size_t)r * d + c], iwl, frac) : (signed char)0;
+    }
+}
+// product table of the linear map: one int8 row of DP outputs per (input dim j, input code v)
+__global__ void k_prep_lut(const float *__restrict__ w, signed char *__restrict__ lut, unsigned d, unsigned DP, int iwl, int frac, int fb)
+{
+    const size_t n = (size_t)d * 255 * DP;
+    const int lim = fixed_max(iwl, frac);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned c = (unsigned)(i % DP);
+        const unsigned jv = (unsigned)(i / DP);
+        const unsigned j = jv / 255;
+        const int v = (int)(jv % 255) - 127;
+        lut[i] = (c < d) ? (signed char)qi_mul(qi_encode(w[(size_t)c * d + j], iwl, frac), v, lim, fb) : (signed char)0;
     }
 }
 // answer projection W stays fp32 (f_fixed = false, MemN2N.c:902-906), rows padded to WS floats
@@ -141,6 +158,112 @@ __device__ __forceinline__ float ldg_stream1(const float *p)
 }
 __device__ __forceinline__ unsigned nzbit(float x) { return ((__float_as_uint(x) << 1) != 0u) ? 1u : 0u; }
 
+// ---- pieces of the row scan --------------------------------------------------------------------
+// True when some lane of the warp holds a value other than 0.0 / 1.0 among its 2*W values
+// (x*x - x == 0 exactly iff x is 0 or 1; one FFMA per value on the FMA pipes, which this kernel leaves idle).
+template <int W>
+__device__ __forceinline__ bool chunk_irregular(const float (&v)[2 * W])
+{
+    unsigned bad = 0;
+#pragma unroll
+    for (int j = 0; j < 2 * W; j++) bad |= __float_as_uint(__fmaf_rn(v[j], v[j], -v[j]));
+    return __any_sync(0xffffffffu, (bad << 1) != 0u);
+}
+
+// Bit j set iff v[j] == 1.0, for values known to be 0.0 or 1.0: sum_j 2^j v[j] formed on top of 2^23, so the
+// integer lands in the low mantissa bits (two FFMA chains, no conversion instruction).
+template <int W>
+__device__ __forceinline__ unsigned unit_mask(const float (&v)[2 * W])
+{
+    if (W == 4) {
+        float s0 = __fmaf_rn(v[0], 1.0f, 8388608.0f), s1 = __fmaf_rn(v[4], 16.0f, 8388608.0f);
+        s0 = __fmaf_rn(v[1], 2.0f, s0);  s1 = __fmaf_rn(v[5], 32.0f, s1);
+        s0 = __fmaf_rn(v[2], 4.0f, s0);  s1 = __fmaf_rn(v[6], 64.0f, s1);
+        s0 = __fmaf_rn(v[3], 8.0f, s0);  s1 = __fmaf_rn(v[7], 128.0f, s1);
+        return (__float_as_uint(s0) | __float_as_uint(s1)) & 0xFFu;
+    }
+    const float s = __fmaf_rn(v[1], 2.0f, v[0] + 8388608.0f);
+    return __float_as_uint(s) & 0x3u;
+}
+
+// Appends one unit entry per set bit of mm (branch-free: idle lanes run the same instructions predicated off).
+template <int W>
+__device__ __forceinline__ unsigned emit_units(unsigned mm, unsigned ca, unsigned cb, unsigned *__restrict__ ent, unsigned cap, unsigned base, unsigned lt)
+{
+    unsigned any;
+    while ((any = __ballot_sync(0xffffffffu, mm != 0u)) != 0u) {
+        const unsigned k = (unsigned)(__ffs((int)mm) - 1);               // garbage when mm == 0, unused
+        const unsigned col = ((k >= (unsigned)W) ? cb : ca) * W + (k & (W - 1));
+        const unsigned pos = base + __popc(any & lt);
+        const unsigned ok = (mm != 0u) & (pos < cap);
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.global.u32 [%1], %2;\n\t}" ::"r"(ok), "l"(ent + pos), "r"(col) : "memory");
+        mm &= mm - 1u;                                                     // 0 stays 0
+        base += __popc(any);
+    }
+    return base;
+}
+
+// General emission of one chunk (MODE 0: unit entries, count splitting, exception entries; MODE 2: {column, bits}
+// pairs into the heap).  Each pass emits one entry per lane that still has something pending.
+template <int W, int MODE>
+__device__ __forceinline__ unsigned emit_general(const CompactParams &p, const float (&v)[2 * W], unsigned ca, unsigned cb, unsigned rix,
+                                                 unsigned *__restrict__ ent, uint2 *__restrict__ heap_dst, unsigned cap, unsigned base, unsigned lt,
+                                                 uint2 *__restrict__ exc, unsigned &n_exc)
+{
+    unsigned m = 0;
+#pragma unroll
+    for (int j = 0; j < 2 * W; j++) m |= nzbit(v[j]) << j;
+    unsigned rep = 0;                            // unit entries still owed for a split count
+    unsigned col = 0;
+    unsigned any;
+    while ((any = __ballot_sync(0xffffffffu, (m | rep) != 0u)) != 0u) {
+        const bool had = ((m | rep) != 0u);
+        const unsigned pos = base + __popc(any & lt);
+        bool unit = true;
+        float x = 1.0f;
+        if (rep) {
+            rep--;                               // another copy of the same column
+        } else if (had) {
+            const unsigned k = (unsigned)(__ffs((int)m) - 1);
+            m &= m - 1u;
+            x = v[0];
+#pragma unroll
+            for (int j = 1; j < 2 * W; j++) x = (k == (unsigned)j) ? v[j] : x;
+            col = ((k >= (unsigned)W) ? cb : ca) * W + (k & (W - 1));
+            unit = (__float_as_uint(x) == 0x3F800000u);
+        }
+        if (MODE == 2) {
+            if (had && pos < cap) heap_dst[pos] = make_uint2(col, __float_as_uint(x));
+        } else {
+            const unsigned bnu = __ballot_sync(0xffffffffu, had && !unit);
+            bool is_exc = false;
+            if (bnu) {                           // some lane holds a value that is not 1.0
+                if (had && !unit) {
+                    const float n = truncf(x);
+                    if (n == x && x >= 2.0f && x <= (float)p.nmax && (unsigned)n * (unsigned)p.colmax[col] <= 127u) rep = (unsigned)n - 1u;
+                    else is_exc = true;
+                }
+                const unsigned bex = __ballot_sync(0xffffffffu, is_exc);
+                if (bex) {
+                    if (is_exc) {
+                        const unsigned xi = n_exc + __popc(bex & lt);
+                        if (xi < MAX_EXC) exc[xi] = make_uint2(rix | (col << 16), __float_as_uint(x));
+                    }
+                    n_exc += __popc(bex);
+                    // exception entries do not occupy the unit list: close the gap they would leave
+                    const unsigned live = any & ~bex;
+                    if (had && !is_exc) { const unsigned pos2 = base + __popc(live & lt); if (pos2 < cap) ent[pos2] = col; }
+                    base += __popc(live);
+                    continue;
+                }
+            }
+            if (had && pos < cap) ent[pos] = col;
+        }
+        base += __popc(any);
+    }
+    return base;
+}
+
 // Scans one row of V floats and appends its entries at `base` (warp-uniform running count).
 // W = floats per load (4: 128-bit loads, needs V % 4 == 0 and 16-byte alignment; 1: scalar).
 // MODE 0: compact record (unit entries, count splitting, exception entries)
@@ -168,62 +291,57 @@ __device__ __forceinline__ unsigned scan_row(const CompactParams &p, const float
             if (ca < VW) v[0] = ldg_stream1(row + ca);
             if (cb < VW) v[1] = ldg_stream1(row + cb);
         }
-        unsigned m = 0;
-#pragma unroll
-        for (int j = 0; j < 2 * W; j++) m |= nzbit(v[j]) << j;
         if (MODE == 1) {
-            base += __reduce_add_sync(0xffffffffu, (unsigned)__popc(m));
-            continue;
-        }
-        // each pass emits one entry per lane that still has something pending; one pass in the common case
-        unsigned rep = 0;                            // unit entries still owed for a split count
-        unsigned col = 0;
-        unsigned any;
-        while ((any = __ballot_sync(0xffffffffu, (m | rep) != 0u)) != 0u) {
-            const bool had = ((m | rep) != 0u);
-            const unsigned pos = base + __popc(any & lt);
-            bool unit = true;
-            float x = 1.0f;
-            if (rep) {
-                rep--;                               // another copy of the same column
-            } else if (had) {
-                const unsigned k = (unsigned)(__ffs((int)m) - 1);
-                m &= m - 1u;
-                x = v[0];
+            unsigned m = 0;
 #pragma unroll
-                for (int j = 1; j < 2 * W; j++) x = (k == (unsigned)j) ? v[j] : x;
-                col = ((k >= (unsigned)W) ? cb : ca) * W + (k & (W - 1));
-                unit = (__float_as_uint(x) == 0x3F800000u);
-            }
-            if (MODE == 2) {
-                if (had && pos < cap) heap_dst[pos] = make_uint2(col, __float_as_uint(x));
-            } else {
-                const unsigned bnu = __ballot_sync(0xffffffffu, had && !unit);
-                bool is_exc = false;
-                if (bnu) {                           // rare: some lane holds a value that is not 1.0
-                    if (had && !unit) {
-                        const float n = truncf(x);
-                        if (n == x && x >= 2.0f && x <= (float)p.nmax && (unsigned)n * (unsigned)p.colmax[col] <= 127u) rep = (unsigned)n - 1u;
-                        else is_exc = true;
-                    }
-                    const unsigned bex = __ballot_sync(0xffffffffu, is_exc);
-                    if (bex) {
-                        if (is_exc) {
-                            const unsigned xi = n_exc + __popc(bex & lt);
-                            if (xi < MAX_EXC) exc[xi] = make_uint2(rix | (col << 16), __float_as_uint(x));
-                        }
-                        n_exc += __popc(bex);
-                        // exception entries do not occupy the unit list: close the gap they would leave
-                        const unsigned live = any & ~bex;
-                        if (had && !is_exc) { const unsigned pos2 = base + __popc(live & lt); if (pos2 < cap) ent[pos2] = col; }
-                        base += __popc(live);
-                        continue;
-                    }
-                }
-                if (had && pos < cap) ent[pos] = col;
-            }
-            base += __popc(any);
+            for (int j = 0; j < 2 * W; j++) m |= nzbit(v[j]) << j;
+            base += __reduce_add_sync(0xffffffffu, (unsigned)__popc(m));
+        } else if (MODE == 0 && !chunk_irregular<W>(v)) {
+            base = emit_units<W>(unit_mask<W>(v), ca, cb, ent, cap, base, lt);     // the common case
+        } else {
+            base = emit_general<W, MODE>(p, v, ca, cb, rix, ent, heap_dst, cap, base, lt, exc, n_exc);
         }
+    }
+    return base;
+}
+
+// MODE-0 scan of a whole story whose rows fit one chunk (V <= 256) with 128-bit loads, software-pipelined: the
+// loads of row r+1 are in flight while row r is classified and emitted (two register stages, unrolled by two so
+// that no register is copied).  FULL: V/4 == 64, no bounds checks.
+template <bool FULL>
+__device__ __forceinline__ unsigned scan_story_pipelined(const CompactParams &p, unsigned story, unsigned S, unsigned long long soff,
+                                                         unsigned *__restrict__ ent, unsigned cap, unsigned short *__restrict__ rend,
+                                                         uint2 *__restrict__ exc, unsigned &n_exc, unsigned lane)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned VW = p.V >> 2;
+    const unsigned ca = lane, cb = lane + 32u;
+    const float4 *qrow = reinterpret_cast<const float4 *>(p.q + (size_t)story * p.V) + lane;
+    const float4 *mrow = reinterpret_cast<const float4 *>(p.m + (size_t)soff * p.V) + lane;     // row r >= 1 is mrow + (r-1)*VW
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load = [&](const float4 *row, float4 &a, float4 &b) {
+        if (FULL) { a = ldg_stream4(row); b = ldg_stream4(row + 32); }
+        else { a = (ca < VW) ? ldg_stream4(row) : zero4; b = (cb < VW) ? ldg_stream4(row + 32) : zero4; }
+    };
+    unsigned base = 0;
+    auto process = [&](const float4 &a, const float4 &b, unsigned r) {
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (!chunk_irregular<4>(v)) base = emit_units<4>(unit_mask<4>(v), ca, cb, ent, cap, base, lt);
+        else base = emit_general<4, 0>(p, v, ca, cb, r, ent, nullptr, cap, base, lt, exc, n_exc);
+        if (lane == 0) rend[r] = (unsigned short)min(base, 0xFFFFu);
+    };
+    float4 a0, b0, a1, b1;
+    load(qrow, a0, b0);
+    unsigned r = 0;
+    for (;;) {
+        if (r < S) load(mrow, a1, b1);            // row r+1
+        process(a0, b0, r);
+        if (++r > S) break;
+        mrow += VW;
+        if (r < S) load(mrow, a0, b0);            // row r+1
+        process(a1, b1, r);
+        if (++r > S) break;
+        mrow += VW;
     }
     return base;
 }
@@ -258,7 +376,13 @@ __global__ void __launch_bounds__(256) k_compact(const CompactParams p)
         unsigned *ent = reinterpret_cast<unsigned *>(rec + p.off_ent);
 
         unsigned n_exc = 0;
-        unsigned n = scan_story<W, 0>(p, story, S, soff, ent, nullptr, p.lcap, rend, exc, n_exc, lane);
+        unsigned n;
+        if (W == 4 && p.V <= 256u) {
+            n = (p.V == 256u) ? scan_story_pipelined<true>(p, story, S, soff, ent, p.lcap, rend, exc, n_exc, lane)
+                              : scan_story_pipelined<false>(p, story, S, soff, ent, p.lcap, rend, exc, n_exc, lane);
+        } else {
+            n = scan_story<W, 0>(p, story, S, soff, ent, nullptr, p.lcap, rend, exc, n_exc, lane);
+        }
         unsigned flags = 0, heap_off = 0;
         if (n > p.lcap || n > 0xFFFFu || n_exc > MAX_EXC) {
             // rare: denser than the fixed slot, or too many exception entries.  Count the raw
@@ -319,9 +443,13 @@ __device__ __forceinline__ int sbyte_prmt(unsigned w)
 }
 
 // v / 2^sh toward zero with a precomputed mask = 2^sh - 1: (v + (v < 0 ? mask : 0)) >> sh
+// (written as PTX: the compiler otherwise strength-reduces the multiply into SHF + LOP3 + IADD, one
+// instruction more on the already saturated ALU pipe)
 __device__ __forceinline__ int shr0m(int v, int sh, int mask)
 {
-    return (int)((unsigned)v >> 31) * mask + v >> sh;
+    int t;
+    asm("{\n\t.reg .u32 s;\n\tshr.u32 s, %1, 31;\n\tmad.lo.s32 %0, s, %2, %1;\n\t}" : "=r"(t) : "r"(v), "r"(mask));
+    return t >> sh;
 }
 // clamp(v, -L, L) + L in one instruction (VIADDMNMX.RELU): max(min(v + L, 2L), 0)
 __device__ __forceinline__ int clamp_biased(int v, int L, int L2) { return __viaddmin_s32_relu(v, L, L2); }
