@@ -60,13 +60,23 @@ struct HopFmt {
 //   mode 2: ub[q][t] = Q_bin(u) as int32                                          MemN2N.c:847
 //   mode 3: av[q][t] = 31-bit magnitude, sv[q][t] = sign word                      layer.c:215-233
 // -------------------------------------------------------------------------------------------------
-__global__ void k_big_prep_query(const signed char *__restrict__ u, int fu, unsigned Q, unsigned d, int mode, HopFmt f,
-                                 int *__restrict__ ub, unsigned *__restrict__ av, unsigned *__restrict__ sv)
+__global__ void __launch_bounds__(256) k_big_prep_query(const signed char *__restrict__ u, int fu, unsigned Q, unsigned d, int mode, HopFmt f,
+                                                        int *__restrict__ ub, unsigned *__restrict__ av, unsigned *__restrict__ sv,
+                                                        signed char *__restrict__ ub8, unsigned *__restrict__ umax)
 {
-    const size_t n = (size_t)Q * d;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // one CTA per query; ub8/umax feed k_big_scores_fast (|Q_bin(u)| <= lb <= 127 fits a byte)
+    __shared__ unsigned s_max;
+    const unsigned q = blockIdx.x;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    unsigned mx = 0;
+    for (unsigned t = threadIdx.x; t < d; t += blockDim.x) {
+        const size_t i = (size_t)q * d + t;
         const int c = (int)u[i];
-        ub[i] = qi_requant(c, fu, f.lb, f.fb);
+        const int b = qi_requant(c, fu, f.lb, f.fb);
+        ub[i] = b;
+        ub8[i] = (signed char)b;
+        mx = max(mx, (unsigned)abs(b));
         if (mode == 3) {
             unsigned s_, m_;
             appx_encode(c, fu, f.ia, s_, m_);
@@ -74,6 +84,10 @@ __global__ void k_big_prep_query(const signed char *__restrict__ u, int fu, unsi
             sv[i] = s_;
         }
     }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_max, mx);
+    __syncthreads();
+    if (threadIdx.x == 0) umax[q] = s_max;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -206,6 +220,187 @@ __global__ void __launch_bounds__(256) k_big_scores(const ScoreParams p)
             }
         }
     }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_big_scores_fast (mode 2, frac_bin == 2, d/16 a power of two): the HBM-bound scorer.
+//
+// Inputs prepared once per memory by k_big_prep_mem: Y = Q_att(M) as int8 (M itself when the re-quantisation is the
+// identity) and rowmax[r] = max_t |Y[r][t]|.  With x_t = y_t * u_t the reference score is
+//   s = Q_att( sum_t Q_att( trunc0(x_t / 4) ) )                                  layer_cuda.cu:105-141
+// and, for a row where no product saturates (rowmax * max|u| <= 4 la + 3),
+//   4 * sum_t trunc0(x_t / 4) = sum_t x_t - sum_t (x_t mod 4) + 4 * #{t : x_t < 0, x_t mod 4 != 0}
+// (floor-mod; trunc0 = floor + 1 exactly for negative non-multiples).  sum_t x_t is one dp4a per four dims.
+// x mod 4 depends on the two low bits of y and u only: bit0 = y0 & u0, bit1 = (y1 & u0) ^ (y0 & u1), evaluated on
+// four packed bytes at once; the sign test is the XOR of the two sign bits.  Per byte the kernel forms
+//   c = (x mod 4) + 3 - 4 [x < 0 and x mod 4 != 0]   in 0..6
+// by clearing bit 2 of (x mod 4) + 3 (a value in 4..6 exactly when x mod 4 != 0), so that
+//   4 * sum = sum_t x_t - sum_t c_t + 3 d.
+// About 10 integer instructions per four products instead of ~28, which moves the kernel from the issue limit to
+// the HBM limit.  Rows that may saturate are recomputed product by product in the same launch.
+//
+// Mapping: LPR = d/16 lanes per row, 32/LPR rows per 512-byte warp load (coalesced 128-bit loads straight from
+// global memory, four in flight per lane, no shared-memory staging); the query operands of QB queries stay in
+// registers for the whole kernel (a lane always sees the same 16 dims).  A warp owns 32 consecutive rows per tile
+// and writes their 32 score bins as one 64-byte segment.
+// -------------------------------------------------------------------------------------------------
+struct FastScoreParams {
+    const signed char *Y;           // [S_local][d] Q_att(M) codes
+    const unsigned char *rowmax;    // [S_local]
+    unsigned long long S_local;
+    unsigned d, Q;
+    int la, fb;
+    const signed char *ub8;         // [Q][d] Q_bin(u)
+    const unsigned *umax;           // [Q] max_t |Q_bin(u)|
+    unsigned short *bins;           // [Q][S_local]
+    unsigned bias;
+};
+
+__device__ __forceinline__ uint4 ldg_stream(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+template <int LPR, int QB>
+__global__ void __launch_bounds__(256) k_big_scores_fast(const FastScoreParams p)
+{
+    constexpr int RPL = 32 / LPR;                 // rows per warp load
+    constexpr int UN = (LPR < 4) ? LPR : 4;       // loads in flight per lane
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned sub = lane % LPR, rsub = lane / LPR;
+    const unsigned q0 = blockIdx.y * QB;
+    const unsigned d = p.d;
+    const int la = p.la;
+    const unsigned sat_lim = 4u * (unsigned)la + 3u;
+
+    unsigned Uw[QB][4], U0[QB][4], U0s[QB][4], U1[QB][4], Us4[QB][4], umax[QB];
+#pragma unroll
+    for (int qi = 0; qi < QB; qi++) {
+        const bool ok = q0 + qi < p.Q;
+        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) t = *reinterpret_cast<const uint4 *>(p.ub8 + (size_t)(q0 + qi) * d + 16u * sub);
+        umax[qi] = ok ? p.umax[q0 + qi] : 0u;
+        const unsigned tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            Uw[qi][w] = tw[w];
+            U0[qi][w] = tw[w] & 0x01010101u;
+            U0s[qi][w] = (tw[w] & 0x01010101u) << 1;
+            U1[qi][w] = tw[w] & 0x02020202u;
+            Us4[qi][w] = (tw[w] >> 5) & 0x04040404u;
+        }
+    }
+
+    const unsigned long long n_tiles = (p.S_local + 31) / 32;
+    const unsigned long long wglobal = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long wstride = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long tix = wglobal; tix < n_tiles; tix += wstride) {
+        const unsigned long long row0 = tix * 32;
+        const unsigned rmv = (row0 + lane < p.S_local) ? (unsigned)p.rowmax[row0 + lane] : 0u;
+        int keep[QB];
+#pragma unroll
+        for (int qi = 0; qi < QB; qi++) keep[qi] = 0;
+#pragma unroll 1
+        for (unsigned it = 0; it < (unsigned)LPR; it += UN) {
+            uint4 y[UN];
+#pragma unroll
+            for (int k = 0; k < UN; k++) {
+                const unsigned long long row = row0 + (unsigned long long)(it + k) * RPL + rsub;
+                y[k] = make_uint4(0u, 0u, 0u, 0u);
+                if (row < p.S_local) y[k] = ldg_stream(p.Y + row * d + 16u * sub);
+            }
+#pragma unroll
+            for (int k = 0; k < UN; k++) {
+                const unsigned yw[4] = {y[k].x, y[k].y, y[k].z, y[k].w};
+                unsigned ys[4], ys4[4];
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    ys[w] = yw[w] << 1;
+                    ys4[w] = (yw[w] >> 5) & 0x04040404u;
+                }
+                const unsigned rm = __shfl_sync(0xffffffffu, rmv, (it + k) * RPL + rsub);
+#pragma unroll
+                for (int qi = 0; qi < QB; qi++) {
+                    int D = 0;
+                    unsigned cs = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        D = __dp4a((int)yw[w], (int)Uw[qi][w], D);
+                        const unsigned t0 = ys[w] & U1[qi][w];
+                        const unsigned t1 = (yw[w] & U0s[qi][w]) ^ t0;
+                        const unsigned bm = (yw[w] & U0[qi][w]) | t1;            // x mod 4 per byte
+                        const unsigned wv = bm + 0x03030303u;                    // 3..6, bit 2 set iff x mod 4 != 0
+                        cs += wv & ~(ys4[w] ^ Us4[qi][w]);                       // clear bit 2 where the product is negative
+                    }
+                    int part = D - (int)__dp4a(cs, 0x01010101u, 0u) + 48;
+#pragma unroll
+                    for (int o = 1; o < LPR; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    int tot = part >> 2;                                         // exact: the numerator is a multiple of 4
+                    const bool risky = rm * umax[qi] > sat_lim;
+                    if (__any_sync(0xffffffffu, risky)) {
+                        // some product of this row may saturate: the reference order of operations, product by product
+                        int sp = 0;
+#pragma unroll
+                        for (int w = 0; w < 4; w++)
+#pragma unroll
+                            for (int b = 0; b < 4; b++) {
+                                const int yy = (int)(signed char)((yw[w] >> (8 * b)) & 0xFFu);
+                                const int uu = (int)(signed char)((Uw[qi][w] >> (8 * b)) & 0xFFu);
+                                sp += qi_mul(yy, uu, la, p.fb);
+                            }
+#pragma unroll
+                        for (int o = 1; o < LPR; o <<= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+                        if (risky) tot = sp;
+                    }
+                    if (sub == it + k) keep[qi] = qi_clamp(tot, la);
+                }
+            }
+        }
+        const unsigned long long row = row0 + sub * RPL + rsub;
+        if (row < p.S_local) {
+#pragma unroll
+            for (int qi = 0; qi < QB; qi++)
+                if (q0 + qi < p.Q) p.bins[(size_t)(q0 + qi) * p.S_local + row] = (unsigned short)(keep[qi] + (int)p.bias);
+        }
+    }
+}
+
+// One warp per row: Y[r][t] = Q_att(M[r][t]) (written when Y != nullptr), rowmax[r] = max_t |Y[r][t]|, and *mismatch
+// is set when some Y differs from its M code (then the scorer needs the copy).
+__global__ void __launch_bounds__(256) k_big_prep_mem(const signed char *__restrict__ M, unsigned long long S, unsigned d, HopFmt f,
+                                                      signed char *__restrict__ Y, unsigned char *__restrict__ rowmax, unsigned *__restrict__ mismatch)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long w0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long ws = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    bool mism = false;
+    for (unsigned long long r = w0; r < S; r += ws) {
+        unsigned mx = 0;
+        for (unsigned c = lane; c < d / 16; c += 32) {
+            const uint4 v = *(reinterpret_cast<const uint4 *>(M + r * d) + c);
+            const unsigned vw[4] = {v.x, v.y, v.z, v.w};
+            unsigned ow[4];
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                unsigned o = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int code = (int)(signed char)((vw[w] >> (8 * b)) & 0xFFu);
+                    const int y = qi_requant(code, f.fw, f.la, f.fa);
+                    mism |= (y != code);
+                    mx = max(mx, (unsigned)abs(y));
+                    o |= ((unsigned)y & 0xFFu) << (8 * b);
+                }
+                ow[w] = o;
+            }
+            if (Y) *(reinterpret_cast<uint4 *>(Y + r * d) + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) rowmax[r] = (unsigned char)mx;
+    }
+    if (__any_sync(0xffffffffu, mism) && lane == 0) atomicOr(mismatch, 1u);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -474,6 +669,13 @@ struct qmann_bigmem {
     int fu;
     int *ub;
     unsigned *av, *sv;
+    signed char *ub8;                // [Q_max][d] Q_bin(u) as bytes (k_big_scores_fast)
+    unsigned *umax;                  // [Q_max] max |Q_bin(u)|
+    // k_big_scores_fast inputs per hop: Y = Q_att(M) (== M when the re-quantisation is the identity), row maxima
+    const signed char *Y[MAXH];
+    signed char *Y_own[MAXH];
+    unsigned char *rowmax[MAXH];
+    bool fast[MAXH];
     unsigned short *bins;            // [Q_max][S_local]
     unsigned char *pq;               // [Q_max][NB]
     unsigned *thr, *nsel;
@@ -502,6 +704,35 @@ static int launch_scores(qmann_bigmem *b, const ScoreParams &sp, cudaStream_t st
     count_launch();
     BCUDA(cudaPeekAtLastError());
     return QMANN_OK;
+}
+
+template <int LPR>
+static int launch_scores_fast(qmann_bigmem *b, const FastScoreParams &fp, cudaStream_t st)
+{
+    const unsigned long long tiles = (fp.S_local + 31) / 32;
+    const bool q4 = fp.Q >= 3;
+    const unsigned qblocks = q4 ? (fp.Q + 3) / 4 : fp.Q;
+    // 8 warps per CTA, one 32-row tile per warp and iteration; enough CTAs to fill every SM several times over
+    unsigned gx = (unsigned)std::min<unsigned long long>((tiles + 7) / 8, (unsigned long long)b->sm_count * 16);
+    gx = std::max(1u, gx);
+    if (q4) k_big_scores_fast<LPR, 4><<<dim3(gx, qblocks), 256, 0, st>>>(fp);
+    else    k_big_scores_fast<LPR, 1><<<dim3(gx, qblocks), 256, 0, st>>>(fp);
+    count_launch();
+    BCUDA(cudaPeekAtLastError());
+    return QMANN_OK;
+}
+
+static int dispatch_scores_fast(qmann_bigmem *b, const FastScoreParams &fp, cudaStream_t st)
+{
+    switch (fp.d / 16) {
+    case 1: return launch_scores_fast<1>(b, fp, st);
+    case 2: return launch_scores_fast<2>(b, fp, st);
+    case 4: return launch_scores_fast<4>(b, fp, st);
+    case 8: return launch_scores_fast<8>(b, fp, st);
+    case 16: return launch_scores_fast<16>(b, fp, st);
+    case 32: return launch_scores_fast<32>(b, fp, st);
+    }
+    return bfail(QMANN_E_ARG, "k_big_scores_fast: d/16 must be a power of two");
 }
 
 extern "C" {
@@ -558,6 +789,8 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
     BCUDA(cudaMalloc((void **)&b->ub, Qd * 4));
     BCUDA(cudaMalloc((void **)&b->av, Qd * 4));
     BCUDA(cudaMalloc((void **)&b->sv, Qd * 4));
+    BCUDA(cudaMalloc((void **)&b->ub8, Qd));
+    BCUDA(cudaMalloc((void **)&b->umax, (size_t)Q_max * 4));
     BCUDA(cudaMalloc((void **)&b->bins, std::max<size_t>(2, (size_t)Q_max * S_local * 2)));
     BCUDA(cudaMalloc((void **)&b->pq, (size_t)Q_max * b->NB));
     BCUDA(cudaMalloc((void **)&b->thr, (size_t)Q_max * 4));
@@ -569,6 +802,40 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
         k_big_quant_H<<<64, 256>>>(w->dev_Hm[h], b->dev_H[h], c.d * c.d, c.iwl_w[h], c.frac_w[h]);
         count_launch();
     }
+    // k_big_scores_fast (mode 2, two fractional bits in the query format, d/16 a power of two): one pass over each
+    // hop's M for the row maxima, and a re-quantised copy only where Q_att(M) differs from M.  The caller's memory
+    // must not change while this object lives.  QMANN_BIGMEM_FAST=0 keeps the per-product kernel (A/B tests).
+    const unsigned c16 = c.d / 16;
+    const char *env_fast = getenv("QMANN_BIGMEM_FAST");
+    const bool want_fast = c.mode == 2 && c.frac_bin == 2 && (c16 & (c16 - 1)) == 0 && c16 <= 32 && S_local > 0 &&
+                           !(env_fast && atoi(env_fast) == 0);
+    if (want_fast) {
+        unsigned *dev_flag = nullptr;
+        BCUDA(cudaMalloc((void **)&dev_flag, 4));
+        const unsigned gx = (unsigned)std::min<unsigned long long>((S_local + 7) / 8, (unsigned long long)b->sm_count * 16);
+        for (unsigned h = 0; h < c.H; h++) {
+            BCUDA(cudaMalloc((void **)&b->rowmax[h], S_local));
+            BCUDA(cudaMemset(dev_flag, 0, 4));
+            k_big_prep_mem<<<std::max(1u, gx), 256>>>(b->M[h], S_local, c.d, b->f[h], nullptr, b->rowmax[h], dev_flag);
+            count_launch();
+            unsigned flag = 0;
+            BCUDA(cudaMemcpy(&flag, dev_flag, 4, cudaMemcpyDeviceToHost));
+            b->Y[h] = b->M[h];
+            if (flag) {
+                if (cudaMalloc((void **)&b->Y_own[h], (size_t)S_local * c.d) != cudaSuccess) {
+                    cudaGetLastError();                      // no room for the copy: this hop keeps the per-product kernel
+                    b->Y_own[h] = nullptr;
+                    continue;
+                }
+                k_big_prep_mem<<<std::max(1u, gx), 256>>>(b->M[h], S_local, c.d, b->f[h], b->Y_own[h], b->rowmax[h], dev_flag);
+                count_launch();
+                b->Y[h] = b->Y_own[h];
+            }
+            b->fast[h] = true;
+        }
+        BCUDA(cudaDeviceSynchronize());
+        cudaFree(dev_flag);
+    }
     BCUDA(cudaDeviceSynchronize());
     *out = b;
     return QMANN_OK;
@@ -578,6 +845,8 @@ void qmann_bigmem_destroy(qmann_bigmem *b)
 {
     if (!b) return;
     cudaFree(b->u_a); cudaFree(b->u_b); cudaFree(b->ub); cudaFree(b->av); cudaFree(b->sv); cudaFree(b->bins);
+    cudaFree(b->ub8); cudaFree(b->umax);
+    for (int h = 0; h < MAXH; h++) { cudaFree(b->Y_own[h]); cudaFree(b->rowmax[h]); }
     cudaFree(b->pq); cudaFree(b->thr); cudaFree(b->nsel); cudaFree(b->zbuf);
     for (int h = 0; h < MAXH; h++) cudaFree(b->dev_H[h]);
     if (b->pev[0]) for (int i = 0; i < 2 * MAXH; i++) cudaEventDestroy(b->pev[i]);
@@ -603,7 +872,7 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned Q = b->Q, d = b->cfg.d;
     const HopFmt &f = b->f[h];
-    k_big_prep_query<<<std::min<unsigned>(256, (Q * d + 255) / 256), 256, 0, st>>>(b->u_a, b->fu, Q, d, (int)b->cfg.mode, f, b->ub, b->av, b->sv);
+    k_big_prep_query<<<Q, 256, 0, st>>>(b->u_a, b->fu, Q, d, (int)b->cfg.mode, f, b->ub, b->av, b->sv, b->ub8, b->umax);
     count_launch();
     BCUDA(cudaMemsetAsync(dev_hist, 0, (size_t)Q * b->NB * 4, st));
     if (b->S_local) {
@@ -614,7 +883,13 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
         int rc;
         const bool prof = b->profile && b->pused + 2 <= 2 * MAXH;
         if (prof) BCUDA(cudaEventRecord(b->pev[b->pused], st));
-        if (b->cfg.mode == 3) rc = (Q >= 4) ? launch_scores<3, 4>(b, sp, st) : launch_scores<3, 1>(b, sp, st);
+        if (b->fast[h]) {
+            FastScoreParams fp;
+            fp.Y = b->Y[h]; fp.rowmax = b->rowmax[h]; fp.S_local = b->S_local; fp.d = d; fp.Q = Q; fp.la = f.la; fp.fb = f.fb;
+            fp.ub8 = b->ub8; fp.umax = b->umax; fp.bins = b->bins; fp.bias = (unsigned)f.la;
+            rc = dispatch_scores_fast(b, fp, st);
+        }
+        else if (b->cfg.mode == 3) rc = (Q >= 4) ? launch_scores<3, 4>(b, sp, st) : launch_scores<3, 1>(b, sp, st);
         else rc = (Q >= 16) ? launch_scores<2, 16>(b, sp, st) : (Q >= 4 ? launch_scores<2, 4>(b, sp, st) : launch_scores<2, 1>(b, sp, st));
         if (rc) return rc;
         if (prof) { BCUDA(cudaEventRecord(b->pev[b->pused + 1], st)); b->pused += 2; }

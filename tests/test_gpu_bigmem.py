@@ -82,6 +82,28 @@ def test_bigmem_matches_oracle(mode, d, S, Q, iwl, qmann, synth, qmo):
     assert ref["nsel"].sum() > 0
 
 
+@pytest.mark.parametrize("d,S,Q,sigma,plant", [(16, 4099, 1, 0.6, 3.0), (32, 3001, 2, 2.0, 3.0), (64, 2050, 5, 0.2, 1.0), (128, 1500, 3, 1.0, 3.0),
+                                                 (256, 1111, 4, 0.6, 3.0), (256, 777, 1, 4.0, 3.0), (512, 515, 7, 0.6, 2.0)])
+def test_bigmem_fast_scorer_equals_per_product(d, S, Q, sigma, plant, qmann, synth, monkeypatch):
+    """k_big_scores_fast (packed low-bit / dp4a form, saturating rows recomputed product by product) against the
+    per-product kernel k_big_scores on the same memory: identical histograms, controller states and answers.
+    sigma = 2..4 makes most rows saturate somewhere (the in-kernel exact path), sigma = 0.2 none."""
+    cfg = synth.ModelConfig(V=40, d=d, S_max=64, V_dict=20, mode=2, iwl=5)
+    w = synth.make_weights(cfg, 5, sigma=0.5)
+    M8, C8, u0 = _random_memory(cfg, S, Q, 900 + d + Q, sigma=sigma, plant_scale=plant)
+    M8[0, 7, :] = -128                      # outside the format: Q_att clamps it to -127 in both kernels
+    M8[1, 11, :3] = 127
+    monkeypatch.setenv("QMANN_BIGMEM_FAST", "0")
+    slow = _run(qmann, cfg, w, M8, C8, u0)
+    monkeypatch.setenv("QMANN_BIGMEM_FAST", "1")
+    fast = _run(qmann, cfg, w, M8, C8, u0)
+    for k in ("hist", "o", "g", "u", "z", "pred"):
+        np.testing.assert_array_equal(fast[k], slow[k], err_msg=k)
+    many = _run(qmann, cfg, w, M8, C8, u0, shards=3)
+    np.testing.assert_array_equal(many["hist"], slow["hist"].astype(np.int64))
+    np.testing.assert_array_equal(many["u"], slow["u"])
+
+
 @pytest.mark.parametrize("mode", [2, 3])
 def test_bigmem_shards_agree(mode, qmann, synth):
     cfg = synth.ModelConfig(V=40, d=64, S_max=64, V_dict=20, mode=mode, iwl=5 if mode == 2 else 3)
