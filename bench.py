@@ -383,6 +383,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--queries", type=int, default=64, help="C5: queries per step")
+    ap.add_argument("--input", default="dense", choices=["dense", "ids"],
+                    help="C1-C4: dense fp32 arenas (the reference boundary format, the headline) or the word-id lists they are "
+                         "built from (SURVEY 8f-1, reported separately, never mixed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
     args = ap.parse_args()
@@ -406,8 +409,13 @@ def main():
     weights = synth.make_weights(cfg, 0x5EED0000 + 1, sigma=SIGMA)
     st = synth.make_stories(cfg, n, 0x5EED1000 + 1 + rank, S=S)        # every rank: its own shard, same size
     model = qlib.Model(cfg, weights, device=f"cuda:{local}")
-    db = model.upload(st)
+    use_ids = args.input == "ids"
+    ist = synth.ids_from_dense(st) if use_ids else None
+    db = model.upload_ids(ist) if use_ids else model.upload(st)
     stream = torch.cuda.current_stream()
+    # the id lists of a step (~16 MB) fit the 126 MB L2: evict them between timed steps by writing a 512 MB buffer
+    # (outside the per-step events); the dense arenas (1 GB) are larger than L2 and need no flush
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local}") if use_ids else None
 
     def barrier():
         if world > 1:
@@ -427,12 +435,22 @@ def main():
     launches0 = qlib.lib().qmann_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record(stream)
-    for _ in range(K):
-        model.forward(db, with_answers=False)
-    ev1.record(stream)
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    if use_ids:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for a_, b_ in evs:
+            flush.zero_()
+            a_.record(stream)
+            model.forward(db, with_answers=False)
+            b_.record(stream)
+        barrier()
+        ms_total = sum(a_.elapsed_time(b_) for a_, b_ in evs)
+    else:
+        ev0.record(stream)
+        for _ in range(K):
+            model.forward(db, with_answers=False)
+        ev1.record(stream)
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
     launches = qlib.lib().qmann_launch_count() - launches0
     ms_compact, ms_forward, pairs = model.profile_read()
     model.profile(False)
@@ -445,21 +463,29 @@ def main():
     pred_dev = db.pred[:n].cpu().numpy().astype(np.uint32)
 
     # ---------------- end to end: pinned host arenas in, predictions out ----------------
-    m_pin = torch.from_numpy(st.m).pin_memory()
-    q_pin = torch.from_numpy(st.q).pin_memory()
-    a_pin = torch.from_numpy(st.a).pin_memory()
     Ke = args.e2e_steps or min(K, 8)
+    if use_ids:
+        ids_pin = torch.from_numpy(ist.ids.view(np.int16)).pin_memory().numpy().view(np.uint16)
+        off_pin = torch.from_numpy(ist.row_off.view(np.int32)).pin_memory().numpy().view(np.uint32)
+        ans_pin = torch.from_numpy(ist.ans.view(np.int32)).pin_memory().numpy().view(np.uint32)
+        e2e_call = lambda: model.infer_ids_host(ids_pin, off_pin, ans_pin, st.n_sen)
+        h2d = int(ist.ids.nbytes + ist.row_off.nbytes + ist.ans.nbytes)
+    else:
+        m_pin = torch.from_numpy(st.m).pin_memory()
+        q_pin = torch.from_numpy(st.q).pin_memory()
+        a_pin = torch.from_numpy(st.a).pin_memory()
+        e2e_call = lambda: model.infer_host(m_pin, q_pin, a_pin, st.n_sen)
+        h2d = int(st.m.nbytes + st.q.nbytes + st.a.nbytes)
     for _ in range(2):
-        pred_h, match_h, _ = model.infer_host(m_pin, q_pin, a_pin, st.n_sen)
+        pred_h, match_h, _ = e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
-        pred_h, match_h, _ = model.infer_host(m_pin, q_pin, a_pin, st.n_sen)      # synchronous: returns host predictions
+        pred_h, match_h, _ = e2e_call()      # synchronous: returns host predictions
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / Ke
     assert np.array_equal(pred_h, pred_dev), "end-to-end predictions differ from the device-resident pass"
     assert match_h == int((pred_h == st.ans).sum())
-    h2d = int(st.m.nbytes + st.q.nbytes + st.a.nbytes)
     d2h = int(4 * n + 4)
 
     # ---------------- max over ranks ----------------
@@ -479,6 +505,9 @@ def main():
         e2e_value = total_stories / (e2e_ms / 1e3)
         # algorithmic bytes per story (primary model): dense fp32 BoW rows + question in, 4-byte answer out
         bytes_story = 4 * cfg.V * (S + 1) + 4
+        if use_ids:
+            # secondary model: the id lists and their row offsets in, 4-byte answer out
+            bytes_story = (ist.ids.nbytes + ist.row_off.nbytes) / n + 4
         peak, peak_src = measured_peak()
         launches_per_step = pairs / K
         stories_per_launch = n / max(1.0, launches_per_step)
@@ -496,6 +525,9 @@ def main():
             "whole_step_GB/s": bytes_story * n / (ms_step / 1e3) / 1e9,
             "whole_step_frac": bytes_story * n / (ms_step / 1e3) / 1e9 / peak,
         }
+        if use_ids:
+            roofline["note"] = ("word-id input: ~0.6 KB per story, so the HBM roofline is out of reach by construction; the step is "
+                                "bound by the instruction issue rate of k_forward_fast (profiles/: smsp__issue_active)")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             probe, _, threads, _ = cpu_oracle_rate(synth, cfg, weights, S, 64)
@@ -509,11 +541,16 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}; {n} stories per GPU per step",
                        "weights": f"N(0,{SIGMA}), layer-wise tied, EN_MQ formats (6,1)/(5,2)/(4,3), base (5,2)",
-                       "input_format": "dense fp32 bag-of-words arenas (reference boundary format), resident in HBM",
-                       "l2": f"inputs {bytes_story * n / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                       "input_format": ("word-id lists (uint16 ids + uint32 row offsets, SURVEY 8f-1: the lists sample_vectorization scatters "
+                                        "into the dense arenas), resident in HBM") if use_ids else
+                                       "dense fp32 bag-of-words arenas (reference boundary format), resident in HBM",
+                       "l2": (f"inputs {bytes_story * n / 1e6:.0f} MB per step < 126 MB L2: a 512 MB buffer is written between timed steps "
+                              "(outside the per-step CUDA events) to evict them") if use_ids else
+                             f"inputs {bytes_story * n / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "steps": Ke, "api": "qmann_infer_host (pinned host arenas in, host predictions + match count out)"},
+                    "steps": Ke, "api": ("qmann_infer_ids_host (pinned host id lists in, host predictions + match count out)" if use_ids else
+                            "qmann_infer_host (pinned host arenas in, host predictions + match count out)")},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -208,6 +208,18 @@ int  qmann_forward_batch(qmann_model *m, const qmann_batch *b, const float *dev_
 int  qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, const float *a_host,
                       const uint32_t *n_sen, uint32_t N, uint32_t *pred_host, uint32_t *match, float *cost);
 
+/* Word-id input: the lists MemN2N/sample.c:413-575 (sample_vectorization) scatters into
+ * the dense arenas, before the scatter.  Rows are story-major: for story i the question row, then its n_sen[i]
+ * sentence rows (N + sum_sen rows in all).  row_off[r] .. row_off[r+1] delimit row r inside ids[]; every
+ * occurrence of an id adds 1.0 to that column of the row (sample.c:547-568), a sentence's time column
+ * V_dict + n_sen-1-j (sample.c:474) is one more id of its row.  ans[i] is the answer column of story i (or NULL).
+ * Same outputs and the same arithmetic as qmann_forward_batch on the equivalent dense arenas; ids must be < V. */
+int  qmann_forward_ids(qmann_model *m, const qmann_batch *b, const uint16_t *dev_ids, const uint32_t *dev_row_off,
+                       const uint32_t *dev_ans, uint32_t *dev_pred, float *dev_h_true, uint32_t *dev_match,
+                       const qmann_debug *dbg, void *stream);
+int  qmann_infer_ids_host(qmann_model *m, const uint16_t *ids_host, const uint32_t *row_off_host, const uint32_t *ans_host,
+                          const uint32_t *n_sen, uint32_t N, uint32_t *pred_host, uint32_t *match, float *cost);
+
 /* Contiguous story range [first, first+count) for `rank` of `world`, balanced by sentence count
  * (batch sharding across GPUs: stories are independent, no collective). */
 int  qmann_shard_plan(const uint32_t *n_sen, uint32_t N, uint32_t world, uint32_t rank,

@@ -90,6 +90,11 @@ struct qmann_model {
     size_t e2e_m_cap = 0, e2e_n_cap = 0;
     cudaStream_t e2e_compute = nullptr, e2e_copy = nullptr;
     std::vector<cudaEvent_t> e2e_events;
+    // qmann_infer_ids_host staging (grow-only)
+    uint16_t *ids_dev = nullptr;
+    uint32_t *rowoff_dev = nullptr, *ans_dev = nullptr, *e2e_pred2 = nullptr;
+    float *e2e_h2 = nullptr;
+    size_t ids_cap = 0, rows_cap = 0, e2e_n_cap2 = 0;
     // optional per-kernel timing (qmann_profile_*)
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;     // triples: before compact, between, after forward
@@ -353,6 +358,7 @@ void qmann_model_destroy(qmann_model *m)
     if (!m) return;
     cudaFree(m->dev_img); cudaFree(m->dev_lut); cudaFree(m->dev_rec); cudaFree(m->dev_heap); cudaFree(m->dev_heap_used);
     cudaFree(m->dev_slow_list); cudaFree(m->dev_err); cudaFree(m->dev_colmax);
+    cudaFree(m->ids_dev); cudaFree(m->rowoff_dev); cudaFree(m->ans_dev); cudaFree(m->e2e_pred2); cudaFree(m->e2e_h2);
     cudaFree(m->e2e_m); cudaFree(m->e2e_q); cudaFree(m->e2e_a); cudaFree(m->e2e_h); cudaFree(m->e2e_pred); cudaFree(m->e2e_match);
     if (m->e2e_compute) cudaStreamDestroy(m->e2e_compute);
     if (m->e2e_copy) cudaStreamDestroy(m->e2e_copy);
@@ -389,11 +395,20 @@ void qmann_batch_destroy(qmann_batch *b)
     delete b;
 }
 
+// The two input formats of a batch: the dense fp32 arenas (the reference's boundary, compacted by k_compact) or the
+// word-id lists they are built from (k_ids_compact).  Both produce the same compact records.
+struct FwdInput {
+    const float *dev_m = nullptr, *dev_q = nullptr, *dev_a = nullptr;
+    const uint16_t *dev_ids = nullptr;
+    const uint32_t *dev_row_off = nullptr, *dev_ans = nullptr;
+};
+
 // Forward of stories [first, first+count) of the batch; data pointers are the FULL arenas.
-static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, uint32_t count, const float *dev_m, const float *dev_q,
-                         const float *dev_a, uint32_t *dev_pred, float *dev_h_true, uint32_t *dev_match, const qmann_debug *dbg, cudaStream_t st)
+static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, uint32_t count, const FwdInput &in,
+                         uint32_t *dev_pred, float *dev_h_true, uint32_t *dev_match, const qmann_debug *dbg, cudaStream_t st)
 {
     const bool debug = dbg != nullptr;
+    const float *dev_m = in.dev_m, *dev_q = in.dev_q, *dev_a = in.dev_a;
     const bool vec4 = (m->cfg.V % 4 == 0) && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 16 == 0);
     for (uint32_t s0 = first; s0 < first + count; s0 += m->chunk_cap) {
         const uint32_t n = std::min<uint32_t>(m->chunk_cap, first + count - s0);
@@ -413,8 +428,16 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
             m->prof_used += 3;
             QCUDA(cudaEventRecord(pe[0], st));
         }
-        if (vec4) k_compact<4><<<cblocks, 256, 0, st>>>(cp);
-        else      k_compact<1><<<cblocks, 256, 0, st>>>(cp);
+        if (in.dev_ids) {
+            IdsParams ip;
+            ip.ids = in.dev_ids; ip.row_off = in.dev_row_off; ip.ans = in.dev_ans; ip.sen_off = b->dev_sen_off; ip.V = m->cfg.V;
+            ip.story0 = s0; ip.n_stories = n; ip.rec = m->dev_rec; ip.rec_stride = m->rec_stride; ip.off_rend = m->off_rend;
+            ip.off_exc = m->off_exc; ip.off_ent = m->off_ent; ip.lcap = m->lcap; ip.heap = m->dev_heap; ip.heap_cap = m->heap_cap;
+            ip.heap_used = m->dev_heap_used; ip.colmax = m->dev_colmax; ip.nmax = m->nmax;
+            k_ids_compact<<<cblocks, 256, 0, st>>>(ip);
+        }
+        else if (vec4) k_compact<4><<<cblocks, 256, 0, st>>>(cp);
+        else           k_compact<1><<<cblocks, 256, 0, st>>>(cp);
         count_launch();
         QCUDA(cudaPeekAtLastError());
         if (pe) QCUDA(cudaEventRecord(pe[1], st));
@@ -444,7 +467,21 @@ int qmann_forward_batch(qmann_model *m, const qmann_batch *b, const float *dev_m
     if (!m || !b || !dev_q || (!dev_m && b->sum_sen)) return fail(QMANN_E_ARG, "null argument");
     if (b->max_sen > m->cfg.S_max) return fail(QMANN_E_ARG, "a story has more sentences than S_max");
     if (b->N == 0) return QMANN_OK;
-    return forward_range(m, b, 0, b->N, dev_m, dev_q, dev_a, dev_pred, dev_h_true, dev_match, dbg, (cudaStream_t)stream);
+    FwdInput in;
+    in.dev_m = dev_m; in.dev_q = dev_q; in.dev_a = dev_a;
+    return forward_range(m, b, 0, b->N, in, dev_pred, dev_h_true, dev_match, dbg, (cudaStream_t)stream);
+}
+
+int qmann_forward_ids(qmann_model *m, const qmann_batch *b, const uint16_t *dev_ids, const uint32_t *dev_row_off, const uint32_t *dev_ans,
+                      uint32_t *dev_pred, float *dev_h_true, uint32_t *dev_match, const qmann_debug *dbg, void *stream)
+{
+    if (!m || !b || !dev_ids || !dev_row_off) return fail(QMANN_E_ARG, "null argument");
+    if (b->max_sen > m->cfg.S_max) return fail(QMANN_E_ARG, "a story has more sentences than S_max");
+    if (m->cfg.V > 65535u) return fail(QMANN_E_ARG, "ids are 16-bit");
+    if (b->N == 0) return QMANN_OK;
+    FwdInput in;
+    in.dev_ids = dev_ids; in.dev_row_off = dev_row_off; in.dev_ans = dev_ans;
+    return forward_range(m, b, 0, b->N, in, dev_pred, dev_h_true, dev_match, dbg, (cudaStream_t)stream);
 }
 
 int qmann_shard_plan(const uint32_t *n_sen, uint32_t N, uint32_t world, uint32_t rank, uint32_t *first, uint32_t *count)
@@ -517,7 +554,9 @@ int qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, c
         cudaEvent_t ev = m->e2e_events[ev_i++];
         QC2(cudaEventRecord(ev, sx));
         QC2(cudaStreamWaitEvent(sc, ev, 0));
-        rc = forward_range(m, b, s0, n, dm, dq, da, m->e2e_pred, dh, da ? m->e2e_match : nullptr, nullptr, sc);
+        FwdInput in;
+        in.dev_m = dm; in.dev_q = dq; in.dev_a = da;
+        rc = forward_range(m, b, s0, n, in, m->e2e_pred, dh, da ? m->e2e_match : nullptr, nullptr, sc);
         if (rc) { qmann_batch_destroy(b); return rc; }
     }
     QC2(cudaMemcpyAsync(pred_host, m->e2e_pred, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
@@ -538,6 +577,86 @@ int qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, c
         *cost = cacc;
     }
     if (err) return fail(QMANN_E_NOMEM, "a story overflowed the compaction heap");
+    return QMANN_OK;
+}
+
+int qmann_infer_ids_host(qmann_model *m, const uint16_t *ids_host, const uint32_t *row_off_host, const uint32_t *ans_host,
+                         const uint32_t *n_sen, uint32_t N, uint32_t *pred_host, uint32_t *match, float *cost)
+{
+    if (!m || !ids_host || !row_off_host || !n_sen || !pred_host) return fail(QMANN_E_ARG, "null argument");
+    if (m->cfg.V > 65535u) return fail(QMANN_E_ARG, "ids are 16-bit");
+    qmann_batch *b = nullptr;
+    int rc = qmann_batch_create(&b, n_sen, N);
+    if (rc) return rc;
+    if (b->max_sen > m->cfg.S_max) { qmann_batch_destroy(b); return fail(QMANN_E_ARG, "a story has more sentences than S_max"); }
+#define QC2(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { qmann_batch_destroy(b); return fail(QMANN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    const size_t R = (size_t)N + b->sum_sen;                 // rows: one question and n_sen sentences per story
+    const size_t n_ids = row_off_host[R];
+    if (n_ids > m->ids_cap) {
+        cudaFree(m->ids_dev); m->ids_dev = nullptr; m->ids_cap = 0;
+        QC2(cudaMalloc((void **)&m->ids_dev, std::max<size_t>(1, n_ids) * sizeof(uint16_t)));
+        m->ids_cap = n_ids;
+    }
+    if (R + 1 > m->rows_cap) {
+        cudaFree(m->rowoff_dev); m->rowoff_dev = nullptr; m->rows_cap = 0;
+        QC2(cudaMalloc((void **)&m->rowoff_dev, (R + 1) * sizeof(uint32_t)));
+        m->rows_cap = R + 1;
+    }
+    if (N > m->e2e_n_cap2) {
+        cudaFree(m->ans_dev); cudaFree(m->e2e_h2); cudaFree(m->e2e_pred2);
+        m->ans_dev = nullptr; m->e2e_h2 = nullptr; m->e2e_pred2 = nullptr; m->e2e_n_cap2 = 0;
+        QC2(cudaMalloc((void **)&m->ans_dev, (size_t)N * sizeof(uint32_t)));
+        QC2(cudaMalloc((void **)&m->e2e_h2, (size_t)N * sizeof(float)));
+        QC2(cudaMalloc((void **)&m->e2e_pred2, (size_t)N * sizeof(uint32_t)));
+        m->e2e_n_cap2 = N;
+    }
+    if (!m->e2e_match) QC2(cudaMalloc((void **)&m->e2e_match, sizeof(uint32_t)));
+    if (!m->e2e_compute) QC2(cudaStreamCreateWithFlags(&m->e2e_compute, cudaStreamNonBlocking));
+    if (!m->e2e_copy) QC2(cudaStreamCreateWithFlags(&m->e2e_copy, cudaStreamNonBlocking));
+    cudaStream_t sc = m->e2e_compute, sx = m->e2e_copy;
+    float *dh = (ans_host && cost) ? m->e2e_h2 : nullptr;
+    QC2(cudaMemsetAsync(m->e2e_match, 0, sizeof(uint32_t), sc));
+    // same pipeline as qmann_infer_host: the copy stream runs ahead chunk by chunk
+    const uint32_t CH = 8192;
+    size_t ev_i = 0;
+    for (uint32_t s0 = 0; s0 < N; s0 += CH) {
+        const uint32_t n = std::min<uint32_t>(CH, N - s0);
+        const size_t r0 = b->sen_off[s0] + s0, r1 = b->sen_off[s0 + n] + s0 + n;          // rows of this chunk
+        const size_t i0 = row_off_host[r0], i1 = row_off_host[r1];
+        if (i1 > i0) QC2(cudaMemcpyAsync(m->ids_dev + i0, ids_host + i0, (i1 - i0) * sizeof(uint16_t), cudaMemcpyHostToDevice, sx));
+        QC2(cudaMemcpyAsync(m->rowoff_dev + r0, row_off_host + r0, (r1 - r0 + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sx));
+        if (ans_host) QC2(cudaMemcpyAsync(m->ans_dev + s0, ans_host + s0, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, sx));
+        if (ev_i >= m->e2e_events.size()) {
+            cudaEvent_t ev;
+            QC2(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            m->e2e_events.push_back(ev);
+        }
+        cudaEvent_t ev = m->e2e_events[ev_i++];
+        QC2(cudaEventRecord(ev, sx));
+        QC2(cudaStreamWaitEvent(sc, ev, 0));
+        FwdInput in;
+        in.dev_ids = m->ids_dev; in.dev_row_off = m->rowoff_dev; in.dev_ans = ans_host ? m->ans_dev : nullptr;
+        rc = forward_range(m, b, s0, n, in, m->e2e_pred2, dh, ans_host ? m->e2e_match : nullptr, nullptr, sc);
+        if (rc) { qmann_batch_destroy(b); return rc; }
+    }
+    QC2(cudaMemcpyAsync(pred_host, m->e2e_pred2, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+    uint32_t mt = 0;
+    QC2(cudaMemcpyAsync(&mt, m->e2e_match, sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+    std::vector<float> ht;
+    if (dh) { ht.resize(N); QC2(cudaMemcpyAsync(ht.data(), dh, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, sc)); }
+    unsigned err = 0;
+    QC2(cudaMemcpyAsync(&err, m->dev_err, sizeof(unsigned), cudaMemcpyDeviceToHost, sc));
+    QC2(cudaStreamSynchronize(sc));
+    if (err) QC2(cudaMemset(m->dev_err, 0, sizeof(unsigned)));
+#undef QC2
+    qmann_batch_destroy(b);
+    if (match) *match = mt;
+    if (cost && dh) {
+        float cacc = *cost;
+        for (uint32_t i = 0; i < N; i++) cacc = (float)((double)cacc + -1.0 * (double)ht[i]);
+        *cost = cacc;
+    }
+    if (err) return fail(QMANN_E_ARG, "a story holds an id >= V or overflowed the compaction heap");
     return QMANN_OK;
 }
 

@@ -416,6 +416,176 @@ __global__ void __launch_bounds__(256) k_compact(const CompactParams p)
     }
 }
 
+// =============================================================================================
+// k_ids_compact: word-id lists -> the same compact records.
+// The input is what the reference holds BEFORE sample_vectorization() scatters it into the dense arenas
+// (MemN2N/sample.c:413-575): per row (question, then the story's sentences) the list of column ids, every
+// occurrence adding 1.0 to its column (sample.c:547, :560, :568; a sentence's last id is its time column
+// V_dict + n_sen-1-j, sample.c:474).  An id that occurs n times in a row is the dense value n and is classified
+// exactly like k_compact does: n unit entries when n * colmax <= 127 and n <= nmax, otherwise one exception entry
+// {row | column << 16, (float)n}.  One warp per story; ~0.6 KB read per story instead of 52 KB.
+// =============================================================================================
+struct IdsParams {
+    const unsigned short *ids;         // all rows back to back
+    const unsigned *row_off;           // [N + sum_sen + 1] prefix offsets into ids; story i owns rows sen_off[i]+i .. (question first)
+    const unsigned *ans;               // [N] answer column or NULL
+    const unsigned long long *sen_off;
+    unsigned V;
+    unsigned story0, n_stories;
+    unsigned char *rec;
+    unsigned rec_stride, off_rend, off_exc, off_ent, lcap;
+    uint2 *heap;
+    unsigned long long heap_cap;
+    unsigned long long *heap_used;
+    const unsigned char *colmax;
+    unsigned nmax;
+};
+
+// Classification and emission of the (row, id) occurrences held one per lane (`have` lanes, in row-major order).
+// cnt = occurrences of the id in its row, earlier = an occurrence sits in a lower position of the row.
+// MODE 0: compact record; MODE 1: count the distinct ids per row (= non-zero dense values); MODE 2: {column, fp32 count}
+// pairs into the heap.  Returns the ballot of the lanes that emitted a list entry; base is advanced past them.
+template <int MODE>
+__device__ __forceinline__ unsigned ids_emit(const IdsParams &p, bool have, unsigned id, unsigned row, unsigned cnt, bool earlier,
+                                             unsigned *__restrict__ ent, uint2 *__restrict__ heap_dst, unsigned cap, unsigned &base,
+                                             uint2 *__restrict__ exc, unsigned &n_exc, bool &bad, unsigned lt)
+{
+    const bool oob = have && id >= p.V;
+    bad |= __any_sync(0xffffffffu, oob);
+    const bool ok = have && !oob;
+    unsigned bl;
+    if (MODE == 0) {
+        const bool unit = ok && (cnt == 1u || (cnt <= p.nmax && cnt * (unsigned)p.colmax[id] <= 127u));
+        const bool isx = ok && !unit && !earlier;
+        bl = __ballot_sync(0xffffffffu, unit);
+        const unsigned pos = base + __popc(bl & lt);
+        if (unit && pos < cap) ent[pos] = id;
+        const unsigned bx = __ballot_sync(0xffffffffu, isx);
+        if (bx) {
+            const unsigned xi = n_exc + __popc(bx & lt);
+            if (isx && xi < MAX_EXC) exc[xi] = make_uint2(row | (id << 16), __float_as_uint((float)cnt));
+            n_exc += __popc(bx);
+        }
+    } else {
+        const bool first = ok && !earlier;
+        bl = __ballot_sync(0xffffffffu, first);
+        const unsigned pos = base + __popc(bl & lt);
+        if (MODE == 2 && first && pos < cap) heap_dst[pos] = make_uint2(id, __float_as_uint((float)cnt));
+    }
+    base += __popc(bl);
+    return bl;
+}
+
+// One story.  Rows are packed into tiles: as many whole consecutive rows as hold at most 32 ids together, one id
+// per lane, so that a bAbI-shaped story (rows of ~5 ids) takes ~9 warp steps instead of one per row; duplicates
+// inside a row are found with one match on (row, id).  A row longer than 32 ids is handled alone.
+template <int MODE>
+__device__ __forceinline__ unsigned ids_scan_story(const IdsParams &p, unsigned long long row0, unsigned S, unsigned *__restrict__ ent,
+                                                   uint2 *__restrict__ heap_dst, unsigned cap, unsigned short *__restrict__ rend,
+                                                   uint2 *__restrict__ exc, unsigned &n_exc, bool &bad, unsigned lane)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned base = 0;
+    unsigned ra = 0;                                   // next row (0 = question)
+    while (ra <= S) {
+        const unsigned r = ra + lane;
+        const bool valid = r <= S;
+        const unsigned o_lo = valid ? p.row_off[row0 + r] : 0u;
+        const unsigned o_hi = valid ? p.row_off[row0 + r + 1] : o_lo;
+        const unsigned len = o_hi - o_lo;
+        unsigned incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        const unsigned k = (unsigned)__popc(__ballot_sync(0xffffffffu, valid && incl <= 32u));      // whole rows in this tile
+        const unsigned first_off = __shfl_sync(0xffffffffu, o_lo, 0);
+        if (k == 0) {
+            // row `ra` alone, 32 ids at a time, occurrences counted by walking the row
+            const unsigned L = __shfl_sync(0xffffffffu, len, 0);
+            for (unsigned c0 = 0; c0 < L; c0 += 32) {
+                const unsigned i = c0 + lane;
+                const bool have = i < L;
+                const unsigned id = have ? (unsigned)p.ids[first_off + i] : 0u;
+                unsigned cnt = 0;
+                bool earlier = false;
+                for (unsigned j = 0; j < L; j++) {
+                    const bool same = (unsigned)p.ids[first_off + j] == id;
+                    cnt += same ? 1u : 0u;
+                    earlier |= same && (j < i);
+                }
+                ids_emit<MODE>(p, have, id, ra, cnt, earlier, ent, heap_dst, cap, base, exc, n_exc, bad, lt);
+            }
+            if (MODE != 1 && lane == 0) rend[ra] = (unsigned short)min(base, 0xFFFFu);
+            ra += 1;
+            continue;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, k - 1);
+        const bool have = lane < total;
+        // row of this lane's id inside the tile: j = #{t < k : incl[t] <= lane}
+        unsigned j = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const unsigned t = j + (unsigned)step;
+            const unsigned v = __shfl_sync(0xffffffffu, incl, min(t, 32u) - 1u);
+            if (t <= k && v <= lane) j = t;
+        }
+        const unsigned id = have ? (unsigned)p.ids[first_off + lane] : 0u;
+        const unsigned peers = __match_any_sync(0xffffffffu, have ? ((j << 16) | id) : (0x80000000u | lane));
+        const unsigned base0 = base;
+        const unsigned bl = ids_emit<MODE>(p, have, id, ra + j, (unsigned)__popc(peers), (peers & lt) != 0u, ent, heap_dst, cap, base, exc, n_exc, bad, lt);
+        if (MODE != 1 && lane < k) {
+            const unsigned below = (incl >= 32u) ? 0xFFFFFFFFu : ((1u << incl) - 1u);                 // lanes of rows ra .. ra+lane
+            rend[ra + lane] = (unsigned short)min(base0 + (unsigned)__popc(bl & below), 0xFFFFu);
+        }
+        ra += k;
+    }
+    return base;
+}
+
+__global__ void __launch_bounds__(256) k_ids_compact(const IdsParams p)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < p.n_stories; w += warps) {
+        const unsigned story = p.story0 + w;
+        const unsigned long long soff = p.sen_off[story];
+        const unsigned S = (unsigned)(p.sen_off[story + 1] - soff);
+        const unsigned long long row0 = soff + story;
+        unsigned char *rec = p.rec + (size_t)w * p.rec_stride;
+        unsigned *hdr = reinterpret_cast<unsigned *>(rec);
+        unsigned short *rend = reinterpret_cast<unsigned short *>(rec + p.off_rend);
+        uint2 *exc = reinterpret_cast<uint2 *>(rec + p.off_exc);
+        unsigned *ent = reinterpret_cast<unsigned *>(rec + p.off_ent);
+        unsigned n_exc = 0;
+        bool bad = false;
+        unsigned n = ids_scan_story<0>(p, row0, S, ent, nullptr, p.lcap, rend, exc, n_exc, bad, lane);
+        unsigned flags = 0, heap_off = 0;
+        if (!bad && (n > p.lcap || n > 0xFFFFu || n_exc > MAX_EXC)) {
+            unsigned dummy = 0;
+            n = ids_scan_story<1>(p, row0, S, nullptr, nullptr, 0u, nullptr, nullptr, dummy, bad, lane);
+            unsigned long long off = 0;
+            if (lane == 0) off = atomicAdd(p.heap_used, (unsigned long long)n);
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (n > 0xFFFFu || off + n > p.heap_cap || off + n > 0xFFFFFFFFull) flags = FLAG_ERROR;
+            else {
+                flags = FLAG_HEAP;
+                heap_off = (unsigned)off;
+                ids_scan_story<2>(p, row0, S, nullptr, p.heap + off, n, rend, nullptr, dummy, bad, lane);
+            }
+            n_exc = 0;
+        }
+        if (bad) flags = FLAG_ERROR;
+        unsigned ans = ANS_NONE;
+        if (p.ans) {
+            ans = p.ans[story];
+            if (ans >= p.V) ans = ANS_NONE;
+        }
+        if (lane == 0) { hdr[0] = n; hdr[1] = flags; hdr[2] = ans; hdr[3] = heap_off; hdr[4] = n_exc; }
+    }
+}
+
 // per-column max |code| over an embedding table image (rows of DP int8), folded into colmax[] with max
 __global__ void k_colmax(const signed char *__restrict__ img, unsigned V, unsigned DP, unsigned char *__restrict__ colmax)
 {

@@ -76,6 +76,11 @@ def lib() -> C.CDLL:
     L.qmann_infer_host.restype = C.c_int
     L.qmann_infer_host.argtypes = [C.c_void_p, _FP, _FP, _FP, C.POINTER(_U32), _U32, C.POINTER(_U32), C.POINTER(_U32),
                                    C.POINTER(C.c_float)]
+    L.qmann_forward_ids.restype = C.c_int
+    L.qmann_forward_ids.argtypes = [C.c_void_p, C.c_void_p, _FP, _FP, _FP, _FP, _FP, _FP, C.POINTER(QDebug), C.c_void_p]
+    L.qmann_infer_ids_host.restype = C.c_int
+    L.qmann_infer_ids_host.argtypes = [C.c_void_p, _FP, _FP, _FP, C.POINTER(_U32), _U32, C.POINTER(_U32), C.POINTER(_U32),
+                                       C.POINTER(C.c_float)]
     L.qmann_profile_enable.restype = C.c_int
     L.qmann_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.qmann_profile_read.restype = C.c_int
@@ -202,11 +207,19 @@ class Model:
                 out[k] = torch.zeros(shp, dtype=torch.float32, device=self.device)
                 setattr(dbg, f"dev_{k}", out[k].data_ptr())
         sptr = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        _check(lib().qmann_forward_batch(self._h, db._h, db.m.data_ptr(), db.q.data_ptr(),
-                                         db.a.data_ptr() if with_answers else None, db.pred.data_ptr(),
-                                         db.h_true.data_ptr() if want_h else None,
-                                         db.match.data_ptr() if with_answers else None,
-                                         C.byref(dbg) if dbg is not None else None, C.c_void_p(sptr)))
+        if getattr(db, "ids", None) is not None:
+            # word-id input (qmann_forward_ids): same records, same kernels after the compaction step
+            _check(lib().qmann_forward_ids(self._h, db._h, db.ids.data_ptr(), db.row_off.data_ptr(),
+                                           db.ans.data_ptr() if with_answers else None, db.pred.data_ptr(),
+                                           db.h_true.data_ptr() if want_h else None,
+                                           db.match.data_ptr() if with_answers else None,
+                                           C.byref(dbg) if dbg is not None else None, C.c_void_p(sptr)))
+        else:
+            _check(lib().qmann_forward_batch(self._h, db._h, db.m.data_ptr(), db.q.data_ptr(),
+                                             db.a.data_ptr() if with_answers else None, db.pred.data_ptr(),
+                                             db.h_true.data_ptr() if want_h else None,
+                                             db.match.data_ptr() if with_answers else None,
+                                             C.byref(dbg) if dbg is not None else None, C.c_void_p(sptr)))
         out["match"] = db.match
         out["h_true"] = db.h_true
         return out
@@ -222,6 +235,52 @@ class Model:
                                       pred.ctypes.data_as(C.POINTER(_U32)), C.byref(match),
                                       C.byref(cost) if want_cost else None))
         return pred, int(match.value), float(cost.value)
+
+
+    def upload_ids(self, ist) -> "DeviceIdBatch":
+        return DeviceIdBatch(self, ist)
+
+    def infer_ids_host(self, ids: np.ndarray, row_off: np.ndarray, ans: Optional[np.ndarray], n_sen: np.ndarray, want_cost: bool = False):
+        """Word-id lists in (host), predictions out: qmann_infer_ids_host."""
+        N = len(n_sen)
+        pred = np.zeros(N, dtype=np.uint32)
+        match, cost = _U32(0), C.c_float(0.0)
+        ns = np.ascontiguousarray(n_sen, dtype=np.uint32)
+        assert ids.dtype == np.uint16 and row_off.dtype == np.uint32 and (ans is None or ans.dtype == np.uint32)
+        ptr = lambda x: None if x is None else C.c_void_p(x.ctypes.data if isinstance(x, np.ndarray) else x.data_ptr())
+        _check(lib().qmann_infer_ids_host(self._h, ptr(ids), ptr(row_off), ptr(ans), ns.ctypes.data_as(C.POINTER(_U32)), N,
+                                          pred.ctypes.data_as(C.POINTER(_U32)), C.byref(match),
+                                          C.byref(cost) if want_cost else None))
+        return pred, int(match.value), float(cost.value)
+
+
+class DeviceIdBatch:
+    """Stories as word-id lists resident in HBM (synth.IdStories): the input of qmann_forward_ids."""
+
+    def __init__(self, model: Model, ist):
+        torch = model.torch
+        dev = model.device
+        self.N, self.sum_sen = ist.N, int(ist.n_sen.sum())
+        self.ids = torch.from_numpy(ist.ids.view(np.int16)).to(dev)
+        self.row_off = torch.from_numpy(ist.row_off.view(np.int32)).to(dev)
+        self.ans = torch.from_numpy(ist.ans.astype(np.uint32).view(np.int32)).to(dev)
+        self.pred = torch.zeros(max(1, ist.N), dtype=torch.int32, device=dev)
+        self.h_true = torch.zeros(max(1, ist.N), dtype=torch.float32, device=dev)
+        self.match = torch.zeros(1, dtype=torch.int32, device=dev)
+        ns = np.ascontiguousarray(ist.n_sen, dtype=np.uint32)
+        self._h = C.c_void_p()
+        _check(lib().qmann_batch_create(C.byref(self._h), ns.ctypes.data_as(C.POINTER(_U32)), ist.N))
+
+    def close(self):
+        if self._h:
+            lib().qmann_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class DeviceBatch:

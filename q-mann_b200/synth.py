@@ -158,6 +158,47 @@ def make_stories(cfg: ModelConfig, N: int, seed: int, S: Optional[int] = None, r
     return Stories(m=m, q=q, a=a, n_sen=n_sen, ans=ans)
 
 
+@dataclasses.dataclass
+class IdStories:
+    """The same stories as word-id lists (what MemN2N/sample.c holds before sample_vectorization builds the dense
+    arenas): rows are story-major, question row first, then the story's sentences."""
+    ids: np.ndarray        # [n_ids] uint16
+    row_off: np.ndarray    # [N + sum_sen + 1] uint32
+    ans: np.ndarray        # [N] uint32
+    n_sen: np.ndarray      # [N] uint32
+
+    @property
+    def N(self) -> int:
+        return int(self.n_sen.shape[0])
+
+
+def ids_from_dense(st: Stories) -> IdStories:
+    """Word-id lists whose scatter (every occurrence adds 1.0, MemN2N/sample.c:547-568) reproduces the dense arenas
+    exactly; the arenas must hold non-negative integer counts."""
+    for t in (st.m, st.q):
+        assert np.all(t >= 0) and np.all(t == np.rint(t)), "dense values must be integer counts"
+    N, V = st.N, st.q.shape[1]
+    off = st.offsets()
+    # row order: story i -> question, then sentences off[i] .. off[i+1]
+    n_rows = N + st.sum_sen
+    src = np.empty(n_rows, dtype=np.int64)          # >= 0: sentence row index; < 0: question of story -1 - v
+    first = off[:-1] + np.arange(N)
+    src[first] = -1 - np.arange(N)
+    mask = np.ones(n_rows, dtype=bool)
+    mask[first] = False
+    src[mask] = np.arange(st.sum_sen)
+    dense = np.empty((n_rows, V), dtype=np.int64)
+    dense[first] = st.q.astype(np.int64)
+    dense[mask] = st.m.astype(np.int64)
+    r, c = np.nonzero(dense)
+    rep = dense[r, c]
+    ids = np.repeat(c, rep).astype(np.uint16)
+    per_row = np.bincount(np.repeat(r, rep), minlength=n_rows)
+    row_off = np.zeros(n_rows + 1, dtype=np.uint32)
+    np.cumsum(per_row, out=row_off[1:])
+    return IdStories(ids=ids, row_off=row_off, ans=st.ans.astype(np.uint32), n_sen=st.n_sen.astype(np.uint32))
+
+
 # ---------------------------------------------------------------------------------------------
 # case / dump files exchanged with oracle/ref_harness.c
 # ---------------------------------------------------------------------------------------------
