@@ -302,14 +302,22 @@ __global__ void __launch_bounds__(256) k_big_scores_fast(const FastScoreParams p
         int keep[QB];
 #pragma unroll
         for (int qi = 0; qi < QB; qi++) keep[qi] = 0;
+        const bool full = row0 + 32 <= p.S_local;
+        const signed char *tile_ptr = p.Y + (row0 + rsub) * d + 16u * sub;
 #pragma unroll 1
         for (unsigned it = 0; it < (unsigned)LPR; it += UN) {
             uint4 y[UN];
+            if (full) {
+                // whole tile inside the shard: one 64-bit base per tile, 32-bit offsets per load, no bounds checks
 #pragma unroll
-            for (int k = 0; k < UN; k++) {
-                const unsigned long long row = row0 + (unsigned long long)(it + k) * RPL + rsub;
-                y[k] = make_uint4(0u, 0u, 0u, 0u);
-                if (row < p.S_local) y[k] = ldg_stream(p.Y + row * d + 16u * sub);
+                for (int k = 0; k < UN; k++) y[k] = ldg_stream(tile_ptr + (it + k) * (RPL * d));
+            } else {
+#pragma unroll
+                for (int k = 0; k < UN; k++) {
+                    const unsigned long long row = row0 + (unsigned long long)(it + k) * RPL + rsub;
+                    y[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (row < p.S_local) y[k] = ldg_stream(p.Y + row * d + 16u * sub);
+                }
             }
 #pragma unroll
             for (int k = 0; k < UN; k++) {
@@ -364,6 +372,188 @@ __global__ void __launch_bounds__(256) k_big_scores_fast(const FastScoreParams p
             for (int qi = 0; qi < QB; qi++)
                 if (q0 + qi < p.Q) p.bins[(size_t)(q0 + qi) * p.S_local + row] = (unsigned short)(keep[qi] + (int)p.bias);
         }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_big_scores_mma (mode 2, frac_bin == 2, d % 64 == 0, Q >= 4): the scorer as four int8 tensor-core contractions.
+//
+// With trunc0(x/4) = (x - r)/4, r = sgn(x) * (|x| mod 4) and |x| mod 4 = ((|y| & 3) * (|u| & 3)) & 3 =: rho(a, b):
+//   4 * sum_t trunc0(y_t u_t / 4) = sum_t y_t u_t - sum_{a=1..3} sum_t I_a(y_t) R_a(u_t)
+//   I_a(y) = sgn(y) [ |y| & 3 == a ]  in {-1, 0, 1},   R_a(u) = sgn(u) rho(a, |u| & 3)  in {-3 .. 3}
+// i.e. the [S x d] memory tile times four [d x Q] int8 query planes (u, -R_1, -R_2, -R_3), accumulated exactly in
+// int32: a dense contraction of 4 * S * d * Q multiply-adds per hop (69 G at S = 2^20, d = 256, Q = 64), which is
+// what the tensor cores are for; the CUDA cores only build the three indicator planes of each memory word
+// (~18 integer instructions per four bytes, shared by all Q queries).  Rows that may saturate a product
+// (rowmax * max|u| > 4 la + 3) are recomputed product by product.
+//
+// mma.sync.m16n8k32.s8: a warp owns 16 slots per tile and 64 queries (8 n-tiles, 32 accumulator registers).  The
+// contraction index is permuted so that a lane's A words come from ONE 128-bit load per row and 64-byte step
+// (lane (g, c) reads bytes 64 kk + 16 c .. +15 of rows g and g + 8); k_big_prep_bfrag stores the query planes in
+// the same permutation, already in fragment order, and the kernel copies them linearly into shared memory
+// (1 KB per k-step and n-tile: two conflict-free 128-bit loads per lane bring b0/b1 of all four planes).
+// -------------------------------------------------------------------------------------------------
+constexpr unsigned MMA_QB = 64;                 // queries per block (8 n-tiles)
+
+struct MmaScoreParams {
+    const signed char *Y;
+    const unsigned char *rowmax;
+    unsigned long long S_local;
+    unsigned d, Q;
+    int la, fb;
+    const signed char *ub8;         // [Q][d] (exact recomputation of risky rows)
+    const unsigned *umax;           // [Q]
+    const uint4 *bfrag;             // [qblocks][d/32][8][2][32] fragment-ordered query planes
+    unsigned short *bins;
+    unsigned bias;
+};
+
+__device__ __forceinline__ void mma_s8(int (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// the three indicator planes of four packed codes: I_a = sgn(y) [ |y| & 3 == a ]
+__device__ __forceinline__ void indicator_planes(unsigned yw, unsigned &i1, unsigned &i2, unsigned &i3)
+{
+    unsigned fill;
+    asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(fill) : "r"(yw));           // 0xFF in the bytes that are negative
+    const unsigned a = (((yw ^ fill) & 0x03030303u) + (fill & 0x01010101u)) & 0x03030303u;    // |y| & 3 per byte
+    const unsigned a0 = a & 0x01010101u, a1 = (a >> 1) & 0x01010101u;
+    const unsigned sg = fill | 0x01010101u;                                // 0xFF (-1) or 0x01 (+1) per byte
+    i1 = ((a0 & ~a1) * 0xFFu) & sg;
+    i2 = ((a1 & ~a0) * 0xFFu) & sg;
+    i3 = ((a0 & a1) * 0xFFu) & sg;
+}
+
+__global__ void __launch_bounds__(256, 2) k_big_scores_mma(const MmaScoreParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned g = lane >> 2, c = lane & 3;
+    const unsigned d = p.d, KS = d / 32;                   // k-steps
+    const unsigned q0 = blockIdx.y * MMA_QB;
+    const unsigned frag_vec = KS * 8 * 2 * 32;             // uint4 per query block
+    uint4 *bs = reinterpret_cast<uint4 *>(sm);
+    unsigned *umax_s = reinterpret_cast<unsigned *>(sm + (size_t)frag_vec * 16);
+    {
+        const uint4 *src = p.bfrag + (size_t)blockIdx.y * frag_vec;
+        for (unsigned i = threadIdx.x; i < frag_vec; i += blockDim.x) bs[i] = src[i];
+        for (unsigned i = threadIdx.x; i < MMA_QB; i += blockDim.x) umax_s[i] = (q0 + i < p.Q) ? p.umax[q0 + i] : 0u;
+    }
+    __syncthreads();
+    const int la = p.la;
+    const unsigned sat_lim = 4u * (unsigned)la + 3u;
+    const unsigned long long n_tiles = (p.S_local + 15) / 16;
+    for (unsigned long long tix = (unsigned long long)blockIdx.x * nw + wid; tix < n_tiles; tix += (unsigned long long)gridDim.x * nw) {
+        const unsigned long long rowA = tix * 16 + g, rowB = rowA + 8;
+        const bool okA = rowA < p.S_local, okB = rowB < p.S_local;
+        int acc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[nt][j] = 0;
+        const signed char *pa = p.Y + rowA * d + 16u * c, *pb = p.Y + rowB * d + 16u * c;
+#pragma unroll 1
+        for (unsigned kk0 = 0; kk0 < d / 64; kk0 += 2) {
+            // two 64-byte steps (four k-steps) per iteration: four 128-bit loads in flight per lane
+            uint4 ya[2], yb[2];
+#pragma unroll
+            for (int s2 = 0; s2 < 2; s2++) {
+                const unsigned kk = kk0 + s2;
+                ya[s2] = make_uint4(0u, 0u, 0u, 0u);
+                yb[s2] = make_uint4(0u, 0u, 0u, 0u);
+                if (kk < d / 64) {
+                    if (okA) ya[s2] = ldg_stream(pa + 64u * kk);
+                    if (okB) yb[s2] = ldg_stream(pb + 64u * kk);
+                }
+            }
+#pragma unroll
+            for (int s2 = 0; s2 < 2; s2++) {
+                const unsigned kk = kk0 + s2;
+                if (kk >= d / 64) break;
+                const unsigned wa[4] = {ya[s2].x, ya[s2].y, ya[s2].z, ya[s2].w};
+                const unsigned wb[4] = {yb[s2].x, yb[s2].y, yb[s2].z, yb[s2].w};
+#pragma unroll
+                for (int odd = 0; odd < 2; odd++) {
+                    // A fragments of this k-step: a0/a2 from row g (words 2 odd, 2 odd + 1), a1/a3 from row g + 8
+                    unsigned A[4][4];
+                    A[0][0] = wa[2 * odd]; A[0][2] = wa[2 * odd + 1]; A[0][1] = wb[2 * odd]; A[0][3] = wb[2 * odd + 1];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) indicator_planes(A[0][j], A[1][j], A[2][j], A[3][j]);
+                    const unsigned ks = 2 * kk + odd;
+                    const uint4 *bk = bs + (size_t)ks * (8 * 2 * 32) + lane;
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        const uint4 b01 = bk[nt * 64], b23 = bk[nt * 64 + 32];
+                        mma_s8(acc[nt], A[0][0], A[0][1], A[0][2], A[0][3], b01.x, b01.y);
+                        mma_s8(acc[nt], A[1][0], A[1][1], A[1][2], A[1][3], b01.z, b01.w);
+                        mma_s8(acc[nt], A[2][0], A[2][1], A[2][2], A[2][3], b23.x, b23.y);
+                        mma_s8(acc[nt], A[3][0], A[3][1], A[3][2], A[3][3], b23.z, b23.w);
+                    }
+                }
+            }
+        }
+        // epilogue: C fragment (row g | g+8, query nt*8 + 2c | +1)
+        const unsigned rmA = okA ? (unsigned)p.rowmax[rowA] : 0u, rmB = okB ? (unsigned)p.rowmax[rowB] : 0u;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned ql = nt * 8 + 2 * c + (j & 1);
+                const unsigned q = q0 + ql;
+                const bool hi = j >= 2;
+                const unsigned long long row = hi ? rowB : rowA;
+                if (q >= p.Q || !(hi ? okB : okA)) continue;
+                int tot = acc[nt][j] >> 2;                           // exact: the accumulator is a multiple of 4
+                if ((hi ? rmB : rmA) * umax_s[ql] > sat_lim) {
+                    // some product of this (row, query) may saturate: the reference order of operations
+                    const signed char *yr = p.Y + row * d, *ur = p.ub8 + (size_t)q * d;
+                    int sp = 0;
+                    for (unsigned t = 0; t < d; t++) sp += qi_mul((int)yr[t], (int)ur[t], la, p.fb);
+                    tot = sp;
+                }
+                p.bins[(size_t)q * p.S_local + row] = (unsigned short)(qi_clamp(tot, la) + (int)p.bias);
+            }
+        }
+    }
+}
+
+// Query planes of k_big_scores_mma in fragment order.  For query block qb, k-step ks = 2 kk + odd, n-tile nt, half h,
+// lane (g, c): one uint4 = { b0, b1 of plane 2h, b0, b1 of plane 2h+1 } with b0 = dims 64 kk + 16 c + 8 odd + 0..3 and
+// b1 = the next four dims of query qb*64 + nt*8 + g; planes: 0 = u, a = 1..3: -sgn(u) rho(a, |u| & 3).
+__global__ void __launch_bounds__(256) k_big_prep_bfrag(const signed char *__restrict__ ub8, unsigned Q, unsigned d, uint4 *__restrict__ bfrag)
+{
+    const unsigned KS = d / 32;
+    const unsigned per_block = KS * 8 * 2 * 32;
+    const unsigned qblocks = (Q + MMA_QB - 1) / MMA_QB;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < qblocks * per_block; i += gridDim.x * blockDim.x) {
+        const unsigned qb = i / per_block, r = i % per_block;
+        const unsigned ks = r / (8 * 2 * 32), nt = (r / 64) % 8, h = (r / 32) % 2, lane = r % 32;
+        const unsigned g = lane >> 2, c = lane & 3, kk = ks >> 1, odd = ks & 1;
+        const unsigned q = qb * MMA_QB + nt * 8 + g;
+        unsigned w[4] = {0u, 0u, 0u, 0u};
+        if (q < Q) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned plane = 2 * h + (j >> 1), which = j & 1;
+                unsigned word = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int u = (int)ub8[(size_t)q * d + 64 * kk + 16 * c + 8 * odd + 4 * which + t];
+                    int v = u;
+                    if (plane) {
+                        const int sg = (u > 0) - (u < 0);
+                        v = -sg * (int)(((unsigned)plane * ((unsigned)abs(u) & 3u)) & 3u);
+                    }
+                    word |= ((unsigned)v & 0xFFu) << (8 * t);
+                }
+                w[j] = word;
+            }
+        }
+        bfrag[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -671,6 +861,8 @@ struct qmann_bigmem {
     unsigned *av, *sv;
     signed char *ub8;                // [Q_max][d] Q_bin(u) as bytes (k_big_scores_fast)
     unsigned *umax;                  // [Q_max] max |Q_bin(u)|
+    uint4 *bfrag;                    // k_big_scores_mma query planes, fragment order
+    bool mma_ok;
     // k_big_scores_fast inputs per hop: Y = Q_att(M) (== M when the re-quantisation is the identity), row maxima
     const signed char *Y[MAXH];
     signed char *Y_own[MAXH];
@@ -791,6 +983,14 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
     BCUDA(cudaMalloc((void **)&b->sv, Qd * 4));
     BCUDA(cudaMalloc((void **)&b->ub8, Qd));
     BCUDA(cudaMalloc((void **)&b->umax, (size_t)Q_max * 4));
+    {
+        // tensor-core scorer: d a multiple of 64 whose query planes (d * 256 bytes per block of 64 queries) fit shared memory
+        const char *env_mma = getenv("QMANN_BIGMEM_MMA");
+        const size_t frag_bytes = (size_t)c.d * 256;
+        b->mma_ok = c.mode == 2 && c.frac_bin == 2 && c.d % 64 == 0 && frag_bytes + 1024 <= (size_t)b->smem_optin &&
+                    !(env_mma && atoi(env_mma) == 0);
+        if (b->mma_ok) BCUDA(cudaMalloc((void **)&b->bfrag, (size_t)((Q_max + MMA_QB - 1) / MMA_QB) * frag_bytes));
+    }
     BCUDA(cudaMalloc((void **)&b->bins, std::max<size_t>(2, (size_t)Q_max * S_local * 2)));
     BCUDA(cudaMalloc((void **)&b->pq, (size_t)Q_max * b->NB));
     BCUDA(cudaMalloc((void **)&b->thr, (size_t)Q_max * 4));
@@ -845,7 +1045,7 @@ void qmann_bigmem_destroy(qmann_bigmem *b)
 {
     if (!b) return;
     cudaFree(b->u_a); cudaFree(b->u_b); cudaFree(b->ub); cudaFree(b->av); cudaFree(b->sv); cudaFree(b->bins);
-    cudaFree(b->ub8); cudaFree(b->umax);
+    cudaFree(b->ub8); cudaFree(b->umax); cudaFree(b->bfrag);
     for (int h = 0; h < MAXH; h++) { cudaFree(b->Y_own[h]); cudaFree(b->rowmax[h]); }
     cudaFree(b->pq); cudaFree(b->thr); cudaFree(b->nsel); cudaFree(b->zbuf);
     for (int h = 0; h < MAXH; h++) cudaFree(b->dev_H[h]);
@@ -883,7 +1083,24 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
         int rc;
         const bool prof = b->profile && b->pused + 2 <= 2 * MAXH;
         if (prof) BCUDA(cudaEventRecord(b->pev[b->pused], st));
-        if (b->fast[h]) {
+        if (b->fast[h] && b->mma_ok && Q >= 4) {
+            const unsigned qblocks = (Q + MMA_QB - 1) / MMA_QB;
+            const unsigned frag_vec = (d / 32) * 8 * 2 * 32;
+            k_big_prep_bfrag<<<std::min(256u, (qblocks * frag_vec + 255) / 256), 256, 0, st>>>(b->ub8, Q, d, b->bfrag);
+            count_launch();
+            MmaScoreParams mp;
+            mp.Y = b->Y[h]; mp.rowmax = b->rowmax[h]; mp.S_local = b->S_local; mp.d = d; mp.Q = Q; mp.la = f.la; mp.fb = f.fb;
+            mp.ub8 = b->ub8; mp.umax = b->umax; mp.bfrag = b->bfrag; mp.bins = b->bins; mp.bias = (unsigned)f.la;
+            const size_t smem = (size_t)frag_vec * 16 + MMA_QB * 4;
+            BCUDA(cudaFuncSetAttribute(k_big_scores_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned long long tiles = (b->S_local + 15) / 16;
+            const unsigned gx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((tiles + 7) / 8, (unsigned long long)b->sm_count * 2));
+            k_big_scores_mma<<<dim3(gx, qblocks), 256, smem, st>>>(mp);
+            count_launch();
+            BCUDA(cudaPeekAtLastError());
+            rc = QMANN_OK;
+        }
+        else if (b->fast[h]) {
             FastScoreParams fp;
             fp.Y = b->Y[h]; fp.rowmax = b->rowmax[h]; fp.S_local = b->S_local; fp.d = d; fp.Q = Q; fp.la = f.la; fp.fb = f.fb;
             fp.ub8 = b->ub8; fp.umax = b->umax; fp.bins = b->bins; fp.bias = (unsigned)f.la;
