@@ -252,7 +252,8 @@ int  qmann_profile_read(qmann_model *m, float *ms_compact, float *ms_forward, ui
 typedef struct qmann_bigmem qmann_bigmem;
 
 /* dev_M[h], dev_C[h]: int8 codes [S_local][d] in hop h's weight format (iwl_w[h], frac_w[h]) -- what
- * emb_m[h] / emb_c[h] output (MemN2N.c:835-838); not copied, must outlive the object.  w: only dev_Hm[h]
+ * emb_m[h] / emb_c[h] output (MemN2N.c:835-838); not copied, must outlive the object AND stay unchanged while it
+ * lives (create() derives per-row maxima and, where Q_att(M) != M, a re-quantised int8 copy of M from it).  w: only dev_Hm[h]
  * (fp32 [d][d], if cfg.lin_map) and dev_W (fp32 [V][d], may be NULL with cfg.V == 0) are used.
  * d must be a multiple of 16; cfg.S_max is ignored. */
 int  qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann_weights *w,

@@ -32,6 +32,7 @@
 #include "../../include/qmann_abi.h"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -608,16 +609,27 @@ __global__ void __launch_bounds__(256) k_big_hist(const unsigned short *__restri
         for (unsigned i = threadIdx.x; i < NB; i += blockDim.x) hs[i] = 0;
         __syncthreads();
     }
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < S_local; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned v = b[i];
-        if (use_smem) {
-            atomicAdd(&hs[v], 1u);
-        } else {
-            const unsigned act = __activemask();
-            const unsigned peers = __match_any_sync(act, v);
-            if ((threadIdx.x & 31) == (unsigned)(__ffs((int)peers) - 1)) atomicAdd(&hq[v], (unsigned)__popc(peers));
+    auto add = [&](unsigned v, unsigned n) {
+        if (use_smem) atomicAdd(&hs[v], n);
+        else atomicAdd(&hq[v], n);
+    };
+    // eight bins per 128-bit load; equal neighbours (the scores of a query concentrate in a few bins) share one atomic
+    const bool vec = (S_local % 8 == 0) && ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    const unsigned long long n8 = vec ? S_local / 8 : 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(b) + i);
+        const unsigned w[4] = {v4.x, v4.y, v4.z, v4.w};
+        unsigned cur = w[0] & 0xFFFFu, cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned v = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            if (v != cur) { add(cur, cnt); cur = v; cnt = 0; }
+            cnt++;
         }
+        add(cur, cnt);
     }
+    for (unsigned long long i = n8 * 8 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < S_local; i += (unsigned long long)gridDim.x * blockDim.x)
+        add((unsigned)b[i], 1u);
     if (use_smem) {
         __syncthreads();
         for (unsigned i = threadIdx.x; i < NB; i += blockDim.x)
@@ -775,23 +787,36 @@ struct UpdateParams {
 
 __global__ void __launch_bounds__(256) k_big_update(const UpdateParams p)
 {
-    const unsigned q = blockIdx.x;
+    // one CTA per query; a warp per output dim walks its Hm row with coalesced byte loads (the sum of the quantised
+    // products is an exact integer, so the lanes' partial sums may be added in any order)
+    extern __shared__ int ub_s[];
+    const unsigned q = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const HopFmt f = p.f;
-    for (unsigned i = threadIdx.x; i < p.d; i += blockDim.x) {
-        const int o = qi_clamp(p.partial[(size_t)q * p.d + i], f.lf);
-        int a_f, g_w;
+    const unsigned d = p.d;
+    if (p.Hq) {
+        for (unsigned j = threadIdx.x; j < d; j += blockDim.x) ub_s[j] = p.ub[(size_t)q * d + j];
+        __syncthreads();
+    }
+    for (unsigned i = blockIdx.y * nw + wid; i < d; i += gridDim.y * nw) {
+        int g_w, a_f;
         if (p.Hq) {
             int s = 0;
-            for (unsigned j = 0; j < p.d; j++) s += qi_mul((int)p.Hq[(size_t)i * p.d + j], p.ub[(size_t)q * p.d + j], f.lw, f.fb);
+            const signed char *hrow = p.Hq + (size_t)i * d;
+            for (unsigned j = lane; j < d; j += 32) s += qi_mul((int)hrow[j], ub_s[j], f.lw, f.fb);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             g_w = qi_clamp(s, f.lw);
             a_f = qi_requant(g_w, f.fw, f.lf, f.ff);
         } else {
-            g_w = (int)p.u_in[(size_t)q * p.d + i];
+            g_w = (int)p.u_in[(size_t)q * d + i];
             a_f = qi_requant(g_w, p.fu, f.lf, f.ff);
         }
-        p.u_out[(size_t)q * p.d + i] = (signed char)qi_clamp(a_f + o, f.lf);
-        if (p.dbg_o) p.dbg_o[(size_t)q * p.d + i] = (signed char)o;
-        if (p.dbg_g) p.dbg_g[(size_t)q * p.d + i] = (signed char)g_w;
+        if (lane == 0) {
+            const int o = qi_clamp(p.partial[(size_t)q * d + i], f.lf);
+            p.u_out[(size_t)q * d + i] = (signed char)qi_clamp(a_f + o, f.lf);
+            if (p.dbg_o) p.dbg_o[(size_t)q * d + i] = (signed char)o;
+            if (p.dbg_g) p.dbg_g[(size_t)q * d + i] = (signed char)g_w;
+        }
     }
 }
 
@@ -808,14 +833,30 @@ __global__ void k_big_quant_H(const float *__restrict__ w, signed char *__restri
 __global__ void __launch_bounds__(128) k_big_answer(const float *__restrict__ W, const signed char *__restrict__ u, int fu, unsigned Q, unsigned V,
                                                     unsigned d, float *__restrict__ zbuf, unsigned *__restrict__ pred, float *__restrict__ hout)
 {
-    const unsigned q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    // one warp per query (4 per CTA); u as fp32 in shared memory, W rows read with 128-bit loads (d % 16 == 0), the
+    // products added in index order exactly like the reference's thread 0 does
+    extern __shared__ __align__(16) float us_all[];
+    const unsigned wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned q = blockIdx.x * (blockDim.x >> 5) + wid;
     if (q >= Q) return;
-    float *z = zbuf + (size_t)q * V;
+    float *us = us_all + (size_t)wid * d;
     const float inv = 1.0f / (float)(1 << fu);
+    for (unsigned j = lane; j < d; j += 32) us[j] = (float)u[(size_t)q * d + j] * inv;
+    __syncwarp();
+    float *z = zbuf + (size_t)q * V;
     float zmax = -INFINITY;
     for (unsigned i = lane; i < V; i += 32) {
         float acc = 0.0f;
-        for (unsigned j = 0; j < d; j++) acc = __fadd_rn(acc, __fmul_rn(W[(size_t)i * d + j], (float)u[(size_t)q * d + j] * inv));
+        const float4 *wr = reinterpret_cast<const float4 *>(W + (size_t)i * d);
+#pragma unroll 16
+        for (unsigned j4 = 0; j4 < d / 4; j4++) {
+            const float4 w4 = __ldg(wr + j4);
+            const float4 u4 = *reinterpret_cast<const float4 *>(us + 4 * j4);
+            acc = __fadd_rn(acc, __fmul_rn(w4.x, u4.x));
+            acc = __fadd_rn(acc, __fmul_rn(w4.y, u4.y));
+            acc = __fadd_rn(acc, __fmul_rn(w4.z, u4.z));
+            acc = __fadd_rn(acc, __fmul_rn(w4.w, u4.w));
+        }
         z[i] = acc;
         zmax = fmaxf(zmax, acc);
     }
@@ -942,6 +983,7 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
     if (c.d == 0 || c.d % 16 || c.d > 512) return bfail(QMANN_E_ARG, "d must be a multiple of 16 in 16..512");
     if (Q_max == 0 || Q_max > 65535) return bfail(QMANN_E_ARG, "Q_max must be in 1..65535");
     if (slot0 + S_local > S_total) return bfail(QMANN_E_ARG, "shard exceeds the memory");
+    if (w->dev_W && ((uintptr_t)w->dev_W % 16)) return bfail(QMANN_E_ARG, "dev_W must be 16-byte aligned");
     auto okfmt = [](unsigned i, unsigned f) { return i + f >= 1 && i + f <= 7; };
     for (unsigned h = 0; h < c.H; h++)
         if (!okfmt(c.iwl[h], c.frac[h]) || !okfmt(c.iwl_w[h], c.frac_w[h]) || !okfmt(c.iwl_att[h], c.frac_att[h]))
@@ -1154,7 +1196,7 @@ int qmann_bigmem_hop_update(qmann_bigmem *b, uint32_t h, const int32_t *dev_part
     UpdateParams up;
     up.partial = dev_partial; up.u_in = b->u_a; up.u_out = b->u_b; up.ub = b->ub; up.Hq = b->cfg.lin_map ? b->dev_H[h] : nullptr;
     up.d = b->cfg.d; up.fu = b->fu; up.f = b->f[h]; up.dbg_o = dev_o; up.dbg_g = dev_g;
-    k_big_update<<<b->Q, 256, 0, (cudaStream_t)stream>>>(up);
+    k_big_update<<<dim3(b->Q, (b->cfg.d + 7) / 8), 256, (size_t)b->cfg.d * 4, (cudaStream_t)stream>>>(up);
     count_launch();
     BCUDA(cudaPeekAtLastError());
     std::swap(b->u_a, b->u_b);
@@ -1205,7 +1247,7 @@ int qmann_bigmem_finish(qmann_bigmem *b, uint32_t *dev_pred, float *dev_z, float
     if (!b->dev_W || !b->cfg.V) return bfail(QMANN_E_ARG, "the memory was created without an answer projection (dev_W, V)");
     cudaStream_t st = (cudaStream_t)stream;
     float *z = dev_z ? dev_z : b->zbuf;
-    k_big_answer<<<(b->Q * 32 + 127) / 128, 128, 0, st>>>(b->dev_W, b->u_a, b->fu, b->Q, b->cfg.V, b->cfg.d, z, dev_pred, dev_h);
+    k_big_answer<<<(b->Q * 32 + 127) / 128, 128, (size_t)4 * b->cfg.d * 4, st>>>(b->dev_W, b->u_a, b->fu, b->Q, b->cfg.V, b->cfg.d, z, dev_pred, dev_h);
     count_launch();
     BCUDA(cudaPeekAtLastError());
     return QMANN_OK;
