@@ -165,16 +165,34 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
             int ub[16], cub[16];
             unsigned au[16];
             unsigned su_bits = 0;
+            // Mode 3 in nine bits.  The reference compares 31-bit magnitudes |x| * 2^(31-iwl) (layer_cuda.cu:384-428) and
+            // keeps bits 30..24 of their difference (same signs) or sum (opposite signs, whose carry into bit 31 flips the
+            // sign).  Every magnitude is a multiple of 2^23 (codes have at most 7 bits, k = 31-iwl-frac >= 23) or the
+            // saturated 0x7FFFFFFF, whose low 23 one-bits never borrow or carry against multiples of 2^23: so the
+            // element is exact on A = sat9(code << (k-23)) in [-255, 255]:  w = |A_m - A_u|,  e = 127 - ((w >> 1) & 127),
+            // negative iff the signs differ and w < 256.  The -2^iwl -> 0 encode quirk keeps its sign on the
+            // memory side (the sign test uses the code); a query holding it takes the literal path below.
+            // Checked on every pair of 8-bit codes against tests/golden/kat_appx_element.npz.
+            const int sh_m = 8 - p.ia[h] - fw, sh_u = 8 - p.ia[h] - fu;
+            bool fast3 = (MODE == 3) && sh_m >= 0 && sh_u >= 0 && sh_m <= 8 && sh_u <= 8;
+            const bool sat_m = fast3 && ((127 << sh_m) >= 256);
+            int U9[16];
             if (MODE == 3) {
                 const uint4 t = *reinterpret_cast<const uint4 *>(uvec + 16 * q);
                 const unsigned tw[4] = {t.x, t.y, t.z, t.w};
+                bool quirk = false;
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
+                    const int uc = sbyte(tw[j >> 2], j & 3);
                     unsigned s_, m_;
-                    appx_encode(sbyte(tw[j >> 2], j & 3), fu, p.ia[h], s_, m_);     // layer.c:215-233, layer_cuda.cu:2515
+                    appx_encode(uc, fu, p.ia[h], s_, m_);     // layer.c:215-233, layer_cuda.cu:2515
                     au[j] = m_;
                     su_bits |= (s_ >> 31) << j;
+                    const int tu = fast3 ? (uc << sh_u) : 0;
+                    quirk |= (tu == -256);
+                    U9[j] = (16u * q + j < d) ? max(-255, min(tu, 255)) : 255;     // padding dims: w = 255 -> e = 0
                 }
+                fast3 = fast3 && !__any_sync(0xffffffffu, quirk);
             } else {
 #pragma unroll
                 for (int w4 = 0; w4 < 4; w4++) {
@@ -191,7 +209,17 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
                 const unsigned r = r0 + g;
                 embed_fast<LPR>(p, wso, lane, p.offA[h], (r < S) ? (int)(r + 1) : -1, acc, sel);
                 int part = 0;
-                if (MODE == 3) {
+                if (MODE == 3 && fast3) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int n = qi_clamp(acc[j], lw);
+                        int t = n << sh_m;
+                        if (sat_m) t = (t == -256) ? 0 : max(-255, min(t, 255));
+                        const int w = (int)__sad(t, U9[j], 0u);
+                        const int e = ~(w >> 1) & 0x7F;
+                        part += (((n ^ U9[j]) < 0) && (w < 256)) ? -e : e;
+                    }
+                } else if (MODE == 3) {
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         unsigned sm, am;
