@@ -17,7 +17,7 @@ namespace {
 
 // acc[j] = sum over the unit entries of `row` of the int8 table codes of dims 16q..16q+15.
 // Lanes past their row's end gather the all-zero row V through the pseudo entry at `zaddr`.
-template <int LPR>
+template <int LPR, bool PREMUL>
 __device__ __forceinline__ void embed_fast(const FwdParams &p, unsigned ws, unsigned lane, unsigned tab, int row, int acc[16], const int sel[4])
 {
     const unsigned q = lane % LPR;
@@ -36,7 +36,7 @@ __device__ __forceinline__ void embed_fast(const FwdParams &p, unsigned ws, unsi
 #pragma unroll 4
     for (unsigned k = 0; k < maxlen; k++, ea += 4u) {
         const unsigned col = *reinterpret_cast<const unsigned *>(smem + ((k < len) ? ea : zaddr));
-        const uint4 t = *reinterpret_cast<const uint4 *>(smem + tabq + col * p.DP);
+        const uint4 t = *reinterpret_cast<const uint4 *>(smem + tabq + (PREMUL ? col : col * p.DP));     // PREMUL: the list holds column * DP
         acc[0] = __dp4a((int)t.x, sel[0], acc[0]);   acc[1] = __dp4a((int)t.x, sel[1], acc[1]);
         acc[2] = __dp4a((int)t.x, sel[2], acc[2]);   acc[3] = __dp4a((int)t.x, sel[3], acc[3]);
         acc[4] = __dp4a((int)t.y, sel[0], acc[4]);   acc[5] = __dp4a((int)t.y, sel[1], acc[5]);
@@ -72,12 +72,69 @@ __device__ __forceinline__ int score_fast(const int acc[16], const int ub[16], c
     return part;
 }
 
-template <int LPR, int MODE>
+// ---------------------------------------------------------------------------------------------
+// Packed (SWAR) memory embedding + dot-product scorer of k_forward_fast<.., 2, true>.
+//
+// The A_h tables of this kernel's image hold BIASED bytes code + cm_h[column] (cm_h = max |code| of the column), so a
+// row sum is formed on four dims per 32-bit add with no carries between bytes as long as the row's bias
+// B = sum of cm_h over its entries is <= 127 (then the true sum s - B is in [-B, B] and Q_w is the identity).
+// Stories with a row above that bound are left to the unpacked kernel.  From the packed sums:
+//   a = s - B per byte, y = Q_att(a) per byte (ka = 0: a, +1: 2a, -1: trunc0(a/2)), and the score
+//   4 * sum_t trunc0(y_t u_t / 4) = sum y_t u_t - sum (x_t mod 4) + 4 #{x_t < 0, x_t mod 4 != 0}
+// exactly as in k_big_scores_fast (qmann_bigmem.cu), valid when no product saturates: |y_t| < tau(|u_t|) =
+// ceil(512 / |u_t|), tested exactly per byte; a row that fails is recomputed product by product.
+// All byte identities were checked exhaustively on the host before use.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned SW_H = 0x80808080u, SW_L = 0x7F7F7F7Fu, SW_1 = 0x01010101u;
+
+__device__ __forceinline__ unsigned swar_unbias(unsigned s, unsigned Bw) { return ((s | SW_H) - Bw) ^ (~s & SW_H); }
+__device__ __forceinline__ unsigned swar_half0(unsigned a)          // trunc0(a / 2) per signed byte
+{
+    const unsigned neg = (a >> 7) & SW_1;
+    const unsigned t = ((a & SW_L) + neg) ^ (a & SW_H);
+    return ((t >> 1) & SW_L) | (t & SW_H);
+}
+
+struct SwarQuery {                     // per lane: its 16 dims of Q_bin(u), packed
+    unsigned Uw[4], U0[4], U0s[4], U1[4], Us4[4], Tw[4];
+};
+
+// One pass: the packed row sums acc4 of row r (bias Bw replicated per byte) -> 4 * partial score of this lane's 16 dims
+// (+48) and the saturation flag.  y4 returns Q_att(M) for the exact path.
+template <int KA>
+__device__ __forceinline__ int swar_score(const unsigned (&acc4)[4], unsigned Bw, const SwarQuery &sq, unsigned (&y4)[4], unsigned &flag)
+{
+    int D = 0;
+    unsigned cs = 0, f = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const unsigned a = swar_unbias(acc4[w], Bw);
+        unsigned y;
+        if (KA == 0) y = a;
+        else if (KA > 0) y = (a << 1) & 0xFEFEFEFEu;
+        else y = swar_half0(a);
+        y4[w] = y;
+        unsigned fill;
+        asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(fill) : "r"(y));
+        f |= ((y ^ fill) + (fill & SW_1)) + sq.Tw[w];                 // bit 7 of a byte: |y| >= tau
+        D = __dp4a((int)y, (int)sq.Uw[w], D);
+        const unsigned t0 = (y << 1) & sq.U1[w];
+        const unsigned t1 = (y & sq.U0s[w]) ^ t0;
+        const unsigned bm = (y & sq.U0[w]) | t1;                       // x mod 4 per byte
+        const unsigned wv = bm + 0x03030303u;
+        cs += wv & ~(((y >> 5) & 0x04040404u) ^ sq.Us4[w]);
+    }
+    flag = f & SW_H;
+    return D - (int)__dp4a(cs, SW_1, 0u) + 48;
+}
+
+template <int LPR, int MODE, bool SWAR>
 __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__ FwdParams p)
 {
     constexpr int G = 32 / LPR;
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned g = lane / LPR, q = lane % LPR;
+    if (p.work_list && *p.work_count == 0u) return;           // nothing was left to this kernel
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.img);
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
@@ -97,8 +154,12 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
     signed char *ovec = reinterpret_cast<signed char *>(ws + p.o_ovec);
     float *ufl = reinterpret_cast<float *>(ws + p.o_ufl);
     float *zbuf = reinterpret_cast<float *>(ws);      // aliases the entry list (dead by the answer phase)
-    if (lane == 0) *reinterpret_cast<unsigned *>(ws + p.o_zent) = p.V;
+    unsigned char *brow = ws + p.o_brow;               // SWAR: row biases [H][S_pad]
     const unsigned d = p.d, DP = p.DP, V = p.V;
+    if (lane == 0) *reinterpret_cast<unsigned *>(ws + p.o_zent) = SWAR ? V * DP : V;
+    unsigned short *perm = reinterpret_cast<unsigned short *>(ws + p.o_perm);     // SWAR: rows ordered by entry count
+    unsigned *cnt_s = reinterpret_cast<unsigned *>(ws + p.o_cnt);
+    const unsigned lgDP = 31u - (unsigned)__clz((int)DP);
     int sel[4];
     asm volatile("mov.u32 %0, 0x00000001;" : "=r"(sel[0]));
     asm volatile("mov.u32 %0, 0x00000100;" : "=r"(sel[1]));
@@ -110,7 +171,8 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
         unsigned w = 0;
         if (lane == 0) w = atomicAdd(p.counter, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= p.n_stories) break;
+        if (w >= (p.work_list ? *p.work_count : p.n_stories)) break;
+        if (p.work_list) w = p.work_list[w];
         const unsigned story = p.story0 + w;
         const unsigned S = (unsigned)(p.sen_off[story + 1] - p.sen_off[story]);
 
@@ -126,13 +188,70 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
             const unsigned short *rend_g = reinterpret_cast<const unsigned short *>(rec + p.off_rend);
             for (unsigned r = lane; r < S + 1; r += 32) rend_s[r] = rend_g[r];
             const unsigned *ent_g = reinterpret_cast<const unsigned *>(rec + p.off_ent);
-            for (unsigned k = lane; k < n_ent; k += 32) ent_s[k] = ent_g[k];
+            for (unsigned k = lane; k < n_ent; k += 32) ent_s[k] = SWAR ? ent_g[k] * DP : ent_g[k];
+            if (SWAR && lane < 17) cnt_s[lane] = 0;
         }
         __syncwarp();
+        if (SWAR) {
+            // per-row biases of the hops and the narrow test (every row: B <= 127, B << ka <= 127).  cm10[column] packs
+            // the column maxima of up to three hops in 10-bit fields, so one add per entry serves all hops (rows of
+            // more than 8 entries could overflow a field and are not narrow)
+            const unsigned *cm10 = reinterpret_cast<const unsigned *>(smem + p.offCM[0]);
+            bool ok = true;
+            for (unsigned r = lane; r < S; r += 32) {
+                const unsigned e0 = rend_s[r], e1 = rend_s[r + 1];
+                unsigned B10 = 0;
+                for (unsigned e = e0; e < e1; e++) B10 += cm10[ent_s[e] >> lgDP];
+                ok = ok && (e1 - e0 <= 8u);
+                for (unsigned h = 0; h < p.H; h++) {
+                    const unsigned B = (B10 >> (10u * h)) & 0x3FFu;
+                    const int ka = p.fa[h] - p.fw[h];
+                    ok = ok && ((ka > 0 ? (B << ka) : B) <= 127u);
+                    brow[h * p.S_pad + r] = (unsigned char)min(B, 255u);
+                }
+            }
+            if (!__all_sync(0xffffffffu, ok)) {
+                if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = w;
+                continue;
+            }
+            // Rows ordered by entry count (counting sort; narrow rows have at most 8 entries): the G rows of a pass then
+            // have nearly the same length and the gather loop does not idle on the longest one.  Only the order in
+            // which rows are embedded changes; every score is stored at its own row index.
+            for (unsigned r0 = 0; r0 < S; r0 += 32) {
+                const unsigned r = r0 + lane;
+                const unsigned key = (r < S) ? (unsigned)(rend_s[r + 1] - rend_s[r]) : 16u;
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                if (lane == (unsigned)(__ffs((int)peers) - 1)) cnt_s[key] += (unsigned)__popc(peers);
+                __syncwarp();
+            }
+            {
+                const unsigned c = (lane < 17) ? cnt_s[lane] : 0u;
+                unsigned incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((int)lane >= o) incl += t;
+                }
+                __syncwarp();
+                if (lane < 17) cnt_s[lane] = incl - c;
+            }
+            __syncwarp();
+            for (unsigned r0 = 0; r0 < S; r0 += 32) {
+                const unsigned r = r0 + lane;
+                const unsigned key = (r < S) ? (unsigned)(rend_s[r + 1] - rend_s[r]) : 16u;
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                const unsigned base = cnt_s[key];
+                const unsigned rank = (unsigned)__popc(peers & ((1u << lane) - 1u));
+                if (r < S) perm[base + rank] = (unsigned short)r;
+                __syncwarp();
+                if (rank == 0) cnt_s[key] = base + (unsigned)__popc(peers);
+                __syncwarp();
+            }
+        }
 
         int acc[16];
         // ---- question embedding u0 = Q_w0(sum)                                 MemN2N.c:826, layer_cuda.cu:49 ----
-        embed_fast<LPR>(p, wso, lane, p.offB, (g == 0) ? 0 : -1, acc, sel);
+        embed_fast<LPR, SWAR>(p, wso, lane, p.offB, (g == 0) ? 0 : -1, acc, sel);
         if (g == 0) {
             unsigned packed[4];
 #pragma unroll
@@ -204,10 +323,73 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
             }
 
             // ---- memory embedding + addressing, G rows per pass ----
+            if (SWAR) {
+                SwarQuery sq;
+                {
+                    // Q_bin(u) and the saturation thresholds as bytes, built once per hop by the whole warp in the (idle until
+                    // the answer phase) ufl region, then 16 bytes per lane
+                    const unsigned char *tau = smem + p.offTAU;
+                    unsigned char *ub8_s = reinterpret_cast<unsigned char *>(ufl), *tw_s = ub8_s + DP;
+                    for (unsigned j = lane; j < DP; j += 32) {
+                        const int u = ub32[j];
+                        ub8_s[j] = (unsigned char)(u & 0xFF);
+                        tw_s[j] = tau[abs(u)];
+                    }
+                    __syncwarp();
+                    const uint4 u4 = *reinterpret_cast<const uint4 *>(ub8_s + 16u * q), t4 = *reinterpret_cast<const uint4 *>(tw_s + 16u * q);
+                    const unsigned uw4[4] = {u4.x, u4.y, u4.z, u4.w}, tw4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; w4++) {
+                        const unsigned uw = uw4[w4];
+                        sq.Uw[w4] = uw; sq.Tw[w4] = tw4[w4];
+                        sq.U0[w4] = uw & SW_1; sq.U0s[w4] = (uw & SW_1) << 1; sq.U1[w4] = uw & 0x02020202u;
+                        sq.Us4[w4] = (uw >> 5) & 0x04040404u;
+                    }
+                    __syncwarp();
+                }
+                const unsigned tabq = p.offA[h] + 16u * q;
+                const unsigned zaddr = wso + p.o_zent;
+#pragma unroll 1
+                for (unsigned r0 = 0; r0 < S; r0 += G) {
+                    const unsigned r = (r0 + g < S) ? (unsigned)perm[r0 + g] : S;
+                    unsigned beg = 0, len = 0, Bw = 0;
+                    if (r < S) {
+                        beg = rend_s[r];
+                        len = rend_s[r + 1] - beg;
+                        Bw = (unsigned)brow[h * p.S_pad + r] * SW_1;
+                    }
+                    const unsigned maxlen = __reduce_max_sync(0xffffffffu, len);
+                    unsigned acc4[4] = {0u, 0u, 0u, 0u};
+                    unsigned ea = wso + 4u * beg;
+#pragma unroll 2
+                    for (unsigned k = 0; k < maxlen; k++, ea += 4u) {
+                        const unsigned coff = *reinterpret_cast<const unsigned *>(smem + ((k < len) ? ea : zaddr));
+                        const uint4 t = *reinterpret_cast<const uint4 *>(smem + tabq + coff);
+                        acc4[0] += t.x; acc4[1] += t.y; acc4[2] += t.z; acc4[3] += t.w;
+                    }
+                    unsigned y4[4], flag;
+                    int part;
+                    if (ka == 0) part = swar_score<0>(acc4, Bw, sq, y4, flag);
+                    else if (ka > 0) part = swar_score<1>(acc4, Bw, sq, y4, flag);
+                    else part = swar_score<-1>(acc4, Bw, sq, y4, flag);
+                    int tot = group_sum<LPR>(part) >> 2;               // exact: a multiple of 4
+#pragma unroll
+                    for (int o = 1; o < LPR; o <<= 1) flag |= __shfl_xor_sync(0xffffffffu, flag, o);
+                    if (__any_sync(0xffffffffu, flag != 0u)) {
+                        // some product of this row saturates: the reference order, product by product
+                        int sp = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) sp += qi_mul(sbyte(y4[j >> 2], j & 3), ub[j], la, fb);
+                        sp = group_sum<LPR>(sp);
+                        if (flag) tot = sp;
+                    }
+                    if (q == 0 && r < S) sc[r] = qi_clamp(tot, la);
+                }
+            } else
 #pragma unroll 1
             for (unsigned r0 = 0; r0 < S; r0 += G) {
                 const unsigned r = r0 + g;
-                embed_fast<LPR>(p, wso, lane, p.offA[h], (r < S) ? (int)(r + 1) : -1, acc, sel);
+                embed_fast<LPR, SWAR>(p, wso, lane, p.offA[h], (r < S) ? (int)(r + 1) : -1, acc, sel);
                 int part = 0;
                 if (MODE == 3 && fast3) {
 #pragma unroll
@@ -288,7 +470,7 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
                 const unsigned k = k0 + g;
                 const int r = (k < nnz) ? sc[k] : -1;
                 const int pc = (k < nnz) ? (int)pq[k] : 0;
-                embed_fast<LPR>(p, wso, lane, p.offC[h], (r >= 0) ? r + 1 : -1, acc, sel);
+                embed_fast<LPR, SWAR>(p, wso, lane, p.offC[h], (r >= 0) ? r + 1 : -1, acc, sel);
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const int c_f = qi_requant(qi_clamp(acc[j], lw), fw, lf, ff);

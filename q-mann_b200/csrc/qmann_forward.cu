@@ -81,6 +81,9 @@ struct qmann_model {
     unsigned long long *dev_heap_used;
     unsigned *dev_counter, *dev_slow_count, *dev_counter2, *dev_err;
     unsigned *dev_slow_list = nullptr;       // [chunk_cap] chunk indices the fast kernel left to the general one
+    unsigned *dev_slow_list2 = nullptr;      // [chunk_cap] chunk indices the packed kernel left to the unpacked fast kernel
+    unsigned char *dev_img_swar = nullptr;   // image with biased A_h tables (packed path of k_forward_fast)
+    bool swar_ok = false;
     bool fast_ok = false;                    // every weight format has an integer bit (Q_w(1.0) = 2^frac_w)
     unsigned char *dev_colmax = nullptr;     // [V] max |code| per column over all embedding tables (count splitting)
     unsigned nmax = 0;
@@ -142,27 +145,28 @@ int launch_forward(const qmann_model *m, const FwdParams &p, bool debug, cudaStr
     }
 }
 
-template <int LPR, int MODE>
+template <int LPR, int MODE, bool SWAR>
 int launch_fast_t(const qmann_model *m, const FwdParams &p, cudaStream_t st)
 {
-    QCUDA(cudaFuncSetAttribute(k_forward_fast<LPR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes));
-    k_forward_fast<LPR, MODE><<<(unsigned)m->sm_count, m->NW * 32, m->smem_bytes, st>>>(p);
+    QCUDA(cudaFuncSetAttribute(k_forward_fast<LPR, MODE, SWAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes));
+    k_forward_fast<LPR, MODE, SWAR><<<(unsigned)m->sm_count, m->NW * 32, m->smem_bytes, st>>>(p);
     count_launch();
     QCUDA(cudaPeekAtLastError());
     return QMANN_OK;
 }
 template <int LPR>
-int launch_fast_l(const qmann_model *m, const FwdParams &p, cudaStream_t st)
+int launch_fast_l(const qmann_model *m, const FwdParams &p, bool swar, cudaStream_t st)
 {
-    return m->cfg.mode == 3 ? launch_fast_t<LPR, 3>(m, p, st) : launch_fast_t<LPR, 2>(m, p, st);
+    if (swar) return launch_fast_t<LPR, 2, true>(m, p, st);
+    return m->cfg.mode == 3 ? launch_fast_t<LPR, 3, false>(m, p, st) : launch_fast_t<LPR, 2, false>(m, p, st);
 }
-int launch_fast(const qmann_model *m, const FwdParams &p, cudaStream_t st)
+int launch_fast(const qmann_model *m, const FwdParams &p, bool swar, cudaStream_t st)
 {
     switch (m->LPR) {
-        case 4: return launch_fast_l<4>(m, p, st);
-        case 8: return launch_fast_l<8>(m, p, st);
-        case 16: return launch_fast_l<16>(m, p, st);
-        default: return launch_fast_l<32>(m, p, st);
+        case 4: return launch_fast_l<4>(m, p, swar, st);
+        case 8: return launch_fast_l<8>(m, p, swar, st);
+        case 16: return launch_fast_l<16>(m, p, swar, st);
+        default: return launch_fast_l<32>(m, p, swar, st);
     }
 }
 }  // namespace
@@ -221,6 +225,8 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     for (unsigned h = 0; h < c.H; h++) { p.offA[h] = take((c.V + 1) * DP); p.offC[h] = take((c.V + 1) * DP); }
     for (unsigned h = 0; h < c.H; h++) p.offH[h] = c.lin_map ? take(c.d * HS) : 0;
     p.offW = take(c.V * WS * 4);
+    p.offCM[0] = take((c.V + 1) * 4);                  // cm10[V+1]: column maxima of A_h, three hops per word
+    p.offTAU = take(128);
     p.img_bytes = off;
     p.tables_bytes = off;
     p.V = c.V; p.d = c.d; p.S_max = c.S_max; p.H = c.H; p.lin_map = c.lin_map; p.const_scale = c.const_scale;
@@ -249,7 +255,10 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
         unsigned o_rend = wtake((c.S_max + 2) * 2), o_sc = wtake(S_pad * 4), o_ex = wtake(S_pad * 4), o_pq = wtake(S_pad);
         unsigned o_uvec = wtake(DP), o_ub32 = wtake(DP * 4), o_ovec = wtake(DP), o_ufl = wtake(DP * 4), o_exc = wtake(MAX_EXC * 8);
         unsigned o_zent = wtake(16);
+        unsigned o_brow = wtake(c.H * S_pad);                 // packed path: row biases per hop
+        unsigned o_perm = wtake(S_pad * 2), o_cnt = wtake(20 * 4);        // packed path: rows ordered by length
         fixed_warp = o;
+        p.o_brow = o_brow; p.o_perm = o_perm; p.o_cnt = o_cnt;
         p.o_rend = o_rend; p.o_sc = o_sc; p.o_ex = o_ex; p.o_pq = o_pq; p.o_uvec = o_uvec; p.o_ub32 = o_ub32;
         p.o_ovec = o_ovec; p.o_ufl = o_ufl; p.o_exc = o_exc; p.o_zent = o_zent;
     }
@@ -273,7 +282,7 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     const unsigned ent_region = round_up(std::max(LW * 4, ent_fixed), 16);
     // entry list sits first in the warp scratch; shift the other offsets behind it
     p.o_rend += ent_region; p.o_sc += ent_region; p.o_ex += ent_region; p.o_pq += ent_region; p.o_uvec += ent_region;
-    p.o_ub32 += ent_region; p.o_ovec += ent_region; p.o_ufl += ent_region; p.o_exc += ent_region; p.o_zent += ent_region;
+    p.o_ub32 += ent_region; p.o_ovec += ent_region; p.o_ufl += ent_region; p.o_exc += ent_region; p.o_zent += ent_region; p.o_brow += ent_region; p.o_perm += ent_region; p.o_cnt += ent_region;
     p.warp_bytes = ent_region + fixed_warp;
     p.LW = LW; p.S_pad = S_pad;
     m->NW = NW;
@@ -326,6 +335,28 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
         m->nmax = unit_ok ? nmax : 0;
         m->fast_ok = unit_ok;
     }
+    // packed path (mode 2): every hop with an 8-bit memory/addressing format, two fractional bits in the query operand and
+    // |frac_att - frac_w| <= 1.  QMANN_SWAR=0 keeps the unpacked kernel only (A/B tests).
+    {
+        const char *env_swar = getenv("QMANN_SWAR");
+        bool ok = m->fast_ok && c.mode == 2 && c.frac_bin == 2 && c.H <= 3 && (DP & (DP - 1)) == 0 && !(env_swar && atoi(env_swar) == 0);
+        for (unsigned h = 0; h < c.H && ok; h++) {
+            const int ka = (int)c.frac_att[h] - (int)c.frac_w[h];
+            ok = p.lw[h] == 127 && p.la[h] == 127 && ka >= -1 && ka <= 1;
+        }
+        if (ok) {
+            k_prep_tau<<<1, 128>>>(m->dev_img + p.offTAU);
+            count_launch();
+            QCUDA(cudaMalloc((void **)&m->dev_img_swar, p.img_bytes));
+            QCUDA(cudaMemcpy(m->dev_img_swar, m->dev_img, p.img_bytes, cudaMemcpyDeviceToDevice));
+            for (unsigned h = 0; h < c.H; h++) {
+                k_prep_bias<<<(c.V + 128) / 128, 128>>>(reinterpret_cast<signed char *>(m->dev_img_swar + p.offA[h]),
+                                                        reinterpret_cast<unsigned *>(m->dev_img_swar + p.offCM[0]), h, c.V, DP);
+                count_launch();
+            }
+            m->swar_ok = true;
+        }
+    }
     QCUDA(cudaPeekAtLastError());
     QCUDA(cudaDeviceSynchronize());
     p.img = m->dev_img;
@@ -345,6 +376,7 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     m->dev_slow_count = m->dev_counter + 1;
     m->dev_counter2 = m->dev_counter + 2;
     QCUDA(cudaMalloc((void **)&m->dev_slow_list, (size_t)m->chunk_cap * sizeof(unsigned)));
+    QCUDA(cudaMalloc((void **)&m->dev_slow_list2, (size_t)m->chunk_cap * sizeof(unsigned)));
     QCUDA(cudaMalloc((void **)&m->dev_err, sizeof(unsigned)));
     QCUDA(cudaMemset(m->dev_err, 0, sizeof(unsigned)));
     p.rec = m->dev_rec; p.rec_stride = m->rec_stride; p.off_rend = m->off_rend; p.off_exc = m->off_exc; p.off_ent = m->off_ent;
@@ -357,7 +389,7 @@ void qmann_model_destroy(qmann_model *m)
 {
     if (!m) return;
     cudaFree(m->dev_img); cudaFree(m->dev_lut); cudaFree(m->dev_rec); cudaFree(m->dev_heap); cudaFree(m->dev_heap_used);
-    cudaFree(m->dev_slow_list); cudaFree(m->dev_err); cudaFree(m->dev_colmax);
+    cudaFree(m->dev_slow_list); cudaFree(m->dev_slow_list2); cudaFree(m->dev_img_swar); cudaFree(m->dev_err); cudaFree(m->dev_colmax);
     cudaFree(m->ids_dev); cudaFree(m->rowoff_dev); cudaFree(m->ans_dev); cudaFree(m->e2e_pred2); cudaFree(m->e2e_h2);
     cudaFree(m->e2e_m); cudaFree(m->e2e_q); cudaFree(m->e2e_a); cudaFree(m->e2e_h); cudaFree(m->e2e_pred); cudaFree(m->e2e_match);
     if (m->e2e_compute) cudaStreamDestroy(m->e2e_compute);
@@ -448,9 +480,19 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
         if (dbg) p.dbg = *dbg;
         int rc;
         if (!debug && m->fast_ok) {
-            // regular stories in the small fast kernel; whatever it declines goes through the general one
+            // regular stories in the small fast kernel(s); whatever they decline goes through the general one.
+            // control block: heap_used u64 | counter | slow_count | counter2 | slow_count2 | counter3
+            if (m->swar_ok) {
+                // packed embedding + scorer first; stories with a row whose column maxima add up above 127 go to the unpacked kernel
+                FwdParams ps = p;
+                ps.img = m->dev_img_swar;
+                ps.slow_list = m->dev_slow_list2; ps.slow_count = m->dev_counter + 3;
+                rc = launch_fast(m, ps, true, st);
+                if (rc) return rc;
+                p.work_list = m->dev_slow_list2; p.work_count = m->dev_counter + 3; p.counter = m->dev_counter + 4;
+            }
             p.slow_list = m->dev_slow_list; p.slow_count = m->dev_slow_count;
-            rc = launch_fast(m, p, st);
+            rc = launch_fast(m, p, false, st);
             if (rc) return rc;
             p.work_list = m->dev_slow_list; p.work_count = m->dev_slow_count; p.counter = m->dev_counter2;
         }

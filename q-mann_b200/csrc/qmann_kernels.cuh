@@ -44,6 +44,7 @@ struct FwdParams {
     const unsigned char *img;
     unsigned img_bytes;
     unsigned offB, offA[MAXH], offC[MAXH], offH[MAXH], offW;
+    unsigned offCM[MAXH], offTAU;          // packed path of k_forward_fast: per-column max |code| of A_h, saturation thresholds
     unsigned V, d, S_max, H, lin_map;
     int const_scale;
     unsigned DP, HS, WS;
@@ -60,7 +61,7 @@ struct FwdParams {
     unsigned story0, n_stories, n_total;
     unsigned long long sum_sen;
     // per-warp shared-memory scratch layout (byte offsets inside the warp's scratch)
-    unsigned warp_bytes, LW, S_pad, o_rend, o_sc, o_ex, o_pq, o_uvec, o_ub32, o_ovec, o_ufl, o_exc, o_zent, tables_bytes;
+    unsigned warp_bytes, LW, S_pad, o_rend, o_sc, o_ex, o_pq, o_uvec, o_ub32, o_ovec, o_ufl, o_exc, o_zent, o_brow, o_perm, o_cnt, tables_bytes;
     // outputs
     unsigned *pred;
     float *h_true;
@@ -123,6 +124,27 @@ __global__ void k_prep_ans(const float *__restrict__ w, float *__restrict__ img,
         const unsigned r = (unsigned)(i / WS), c = (unsigned)(i % WS);
         img[i] = (c < d) ? w[(size_t)r * d + c] : 0.0f;
     }
+}
+
+// Packed path of k_forward_fast: cm[v] = max_c |A_h code[v][c]| (packed for up to three hops in the 10-bit fields of
+// cm10[v]) and the A_h table rewritten as code + cm[v] (all DP bytes of a row, so that padding dims unbias to 0); row V
+// stays all-zero with cm = 0.
+__global__ void k_prep_bias(signed char *__restrict__ tab, unsigned *__restrict__ cm10, unsigned hop, unsigned V, unsigned DP)
+{
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v <= V; v += gridDim.x * blockDim.x) {
+        int mx = 0;
+        for (unsigned c = 0; c < DP; c++) mx = max(mx, abs((int)tab[(size_t)v * DP + c]));
+        cm10[v] |= (unsigned)mx << (10u * hop);           // 10-bit field per hop (launches of the hops are serialised)
+        unsigned char *ut = reinterpret_cast<unsigned char *>(tab);
+        for (unsigned c = 0; c < DP; c++) ut[(size_t)v * DP + c] = (unsigned char)((int)tab[(size_t)v * DP + c] + mx);
+    }
+}
+// tau[|u|] = 0x80 - ceil(512 / |u|) (0 for |u| <= 4): a byte |y| + tau[|u|] has bit 7 set iff |y * u| >= 512, i.e. iff the
+// product saturates Q_att (la = 127, two fractional bits in u)
+__global__ void k_prep_tau(unsigned char *__restrict__ tau)
+{
+    const unsigned u = threadIdx.x;
+    if (u < 128) tau[u] = (u <= 4) ? 0 : (unsigned char)(128u - (512u + u - 1u) / u);
 }
 
 // =============================================================================================
