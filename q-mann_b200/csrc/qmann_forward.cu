@@ -442,6 +442,7 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
     const bool debug = dbg != nullptr;
     const float *dev_m = in.dev_m, *dev_q = in.dev_q, *dev_a = in.dev_a;
     const bool vec4 = (m->cfg.V % 4 == 0) && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 16 == 0);
+    const bool vec2 = (m->cfg.V % 2 == 0) && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 8 == 0);
     for (uint32_t s0 = first; s0 < first + count; s0 += m->chunk_cap) {
         const uint32_t n = std::min<uint32_t>(m->chunk_cap, first + count - s0);
         CompactParams cp;
@@ -469,6 +470,7 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
             k_ids_compact<<<cblocks, 256, 0, st>>>(ip);
         }
         else if (vec4) k_compact<4><<<cblocks, 256, 0, st>>>(cp);
+        else if (vec2) k_compact<2><<<cblocks, 256, 0, st>>>(cp);
         else           k_compact<1><<<cblocks, 256, 0, st>>>(cp);
         count_launch();
         QCUDA(cudaPeekAtLastError());

@@ -172,6 +172,12 @@ __device__ __forceinline__ float4 ldg_stream4(const float4 *p)
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ float2 ldg_stream2(const float2 *p)
+{
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ float ldg_stream1(const float *p)
 {
     float r;
@@ -203,6 +209,12 @@ __device__ __forceinline__ unsigned unit_mask(const float (&v)[2 * W])
         s0 = __fmaf_rn(v[2], 4.0f, s0);  s1 = __fmaf_rn(v[6], 64.0f, s1);
         s0 = __fmaf_rn(v[3], 8.0f, s0);  s1 = __fmaf_rn(v[7], 128.0f, s1);
         return (__float_as_uint(s0) | __float_as_uint(s1)) & 0xFFu;
+    }
+    if (W == 2) {
+        float s = __fmaf_rn(v[1], 2.0f, v[0] + 8388608.0f);
+        s = __fmaf_rn(v[2], 4.0f, s);
+        s = __fmaf_rn(v[3], 8.0f, s);
+        return __float_as_uint(s) & 0xFu;
     }
     const float s = __fmaf_rn(v[1], 2.0f, v[0] + 8388608.0f);
     return __float_as_uint(s) & 0x3u;
@@ -287,7 +299,8 @@ __device__ __forceinline__ unsigned emit_general(const CompactParams &p, const f
 }
 
 // Scans one row of V floats and appends its entries at `base` (warp-uniform running count).
-// W = floats per load (4: 128-bit loads, needs V % 4 == 0 and 16-byte alignment; 1: scalar).
+// W = floats per load (4: 128-bit loads, needs V % 4 == 0 and 16-byte alignment; 2: 64-bit loads, V even and 8-byte
+// alignment; 1: scalar).
 // MODE 0: compact record (unit entries, count splitting, exception entries)
 // MODE 1: count the non-zero values only
 // MODE 2: {column, bits} pairs into the heap
@@ -309,6 +322,10 @@ __device__ __forceinline__ unsigned scan_row(const CompactParams &p, const float
             const float4 *r4 = reinterpret_cast<const float4 *>(row);
             if (ca < VW) { const float4 t = ldg_stream4(r4 + ca); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
             if (cb < VW) { const float4 t = ldg_stream4(r4 + cb); v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w; }
+        } else if (W == 2) {
+            const float2 *r2 = reinterpret_cast<const float2 *>(row);
+            if (ca < VW) { const float2 t = ldg_stream2(r2 + ca); v[0] = t.x; v[1] = t.y; }
+            if (cb < VW) { const float2 t = ldg_stream2(r2 + cb); v[2] = t.x; v[3] = t.y; }
         } else {
             if (ca < VW) v[0] = ldg_stream1(row + ca);
             if (cb < VW) v[1] = ldg_stream1(row + cb);
