@@ -105,9 +105,17 @@ struct ScoreParams {
     int const_scale;
     const int *ub;                  // [Q][d]
     const unsigned *av, *sv;        // [Q][d] (mode 3)
-    unsigned short *bins;           // [Q][S_local] score bin = code + bias
+    void *bins;                     // [Q][S_local] score bin = code + bias (uint8 in mode 2, uint16 in mode 3)
+    int bin8;
     unsigned bias;                  // la (mode 2) or 127*d (mode 3)
 };
+
+// score bins are bytes when every bin index fits one (mode 2: 2*127+1 bins), 16-bit otherwise
+__device__ __forceinline__ void store_bin(void *bins, int bin8, size_t idx, unsigned v)
+{
+    if (bin8) reinterpret_cast<unsigned char *>(bins)[idx] = (unsigned char)v;
+    else reinterpret_cast<unsigned short *>(bins)[idx] = (unsigned short)v;
+}
 
 __device__ __forceinline__ int sx8(unsigned w, int b) { return (int)(signed char)((w >> (8 * b)) & 0xFFu); }
 
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(256) k_big_scores(const ScoreParams p)
                     // mode 2: Q_att of the sum; mode 3: the raw sum of e*128 (saturation is applied where the
                     // value is formed, in k_big_softmax)
                     const int code = (MODE == 3) ? acc[q] : qi_clamp(acc[q], f.la);
-                    p.bins[(size_t)(q0 + q) * p.S_local + slot0 + lane] = (unsigned short)(code + (int)p.bias);
+                    store_bin(p.bins, p.bin8, (size_t)(q0 + q) * p.S_local + slot0 + lane, (unsigned)(code + (int)p.bias));
                 }
             }
         }
@@ -253,7 +261,8 @@ struct FastScoreParams {
     int la, fb;
     const signed char *ub8;         // [Q][d] Q_bin(u)
     const unsigned *umax;           // [Q] max_t |Q_bin(u)|
-    unsigned short *bins;           // [Q][S_local]
+    void *bins;                     // [Q][S_local], uint8 (mode 2: 255 bins)
+    int bin8;
     unsigned bias;
 };
 
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(256) k_big_scores_fast(const FastScoreParams p
         if (row < p.S_local) {
 #pragma unroll
             for (int qi = 0; qi < QB; qi++)
-                if (q0 + qi < p.Q) p.bins[(size_t)(q0 + qi) * p.S_local + row] = (unsigned short)(keep[qi] + (int)p.bias);
+                if (q0 + qi < p.Q) store_bin(p.bins, p.bin8, (size_t)(q0 + qi) * p.S_local + row, (unsigned)(keep[qi] + (int)p.bias));
         }
     }
 }
@@ -405,7 +414,8 @@ struct MmaScoreParams {
     const signed char *ub8;         // [Q][d] (exact recomputation of risky rows)
     const unsigned *umax;           // [Q]
     const uint4 *bfrag;             // [qblocks][d/32][8][2][32] fragment-ordered query planes
-    unsigned short *bins;
+    void *bins;
+    int bin8;
     unsigned bias;
 };
 
@@ -427,6 +437,15 @@ __device__ __forceinline__ void indicator_planes(unsigned yw, unsigned &i1, unsi
     i1 = ((a0 & ~a1) * 0xFFu) & sg;
     i2 = ((a1 & ~a0) * 0xFFu) & sg;
     i3 = ((a0 & a1) * 0xFFu) & sg;
+}
+
+// some product of this (row, query) may saturate: the reference order of operations, product by product
+__device__ __noinline__ int exact_row_score(const signed char *__restrict__ yr, const signed char *__restrict__ ur, unsigned d, int la, int fb)
+{
+    int sp = 0;
+#pragma unroll 1
+    for (unsigned t = 0; t < d; t++) sp += qi_mul((int)yr[t], (int)ur[t], la, fb);
+    return sp;
 }
 
 __global__ void __launch_bounds__(256, 2) k_big_scores_mma(const MmaScoreParams p)
@@ -509,14 +528,9 @@ __global__ void __launch_bounds__(256, 2) k_big_scores_mma(const MmaScoreParams 
                 const unsigned long long row = hi ? rowB : rowA;
                 if (q >= p.Q || !(hi ? okB : okA)) continue;
                 int tot = acc[nt][j] >> 2;                           // exact: the accumulator is a multiple of 4
-                if ((hi ? rmB : rmA) * umax_s[ql] > sat_lim) {
-                    // some product of this (row, query) may saturate: the reference order of operations
-                    const signed char *yr = p.Y + row * d, *ur = p.ub8 + (size_t)q * d;
-                    int sp = 0;
-                    for (unsigned t = 0; t < d; t++) sp += qi_mul((int)yr[t], (int)ur[t], la, p.fb);
-                    tot = sp;
-                }
-                p.bins[(size_t)q * p.S_local + row] = (unsigned short)(qi_clamp(tot, la) + (int)p.bias);
+                if ((hi ? rmB : rmA) * umax_s[ql] > sat_lim)
+                    tot = exact_row_score(p.Y + row * d, p.ub8 + (size_t)q * d, d, la, p.fb);    // rare: kept out of line
+                store_bin(p.bins, p.bin8, (size_t)q * p.S_local + row, (unsigned)(qi_clamp(tot, la) + (int)p.bias));
             }
         }
     }
@@ -598,12 +612,15 @@ __global__ void __launch_bounds__(256) k_big_prep_mem(const signed char *__restr
 // k_big_hist: hist[q][bin] += count over this rank's slots.  Small bin counts (mode 2: 255) live in
 // shared memory; large ones (mode 3: 2*127*d+1) use warp-aggregated global atomics.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_big_hist(const unsigned short *__restrict__ bins, unsigned long long S_local, unsigned NB,
+template <typename BinT>
+__global__ void __launch_bounds__(256) k_big_hist(const BinT *__restrict__ bins, unsigned long long S_local, unsigned NB,
                                                   unsigned *__restrict__ hist, int use_smem)
 {
     extern __shared__ unsigned hs[];
+    constexpr unsigned PER = 16 / sizeof(BinT);              // bins per 128-bit load
+    constexpr unsigned BITS = 8 * sizeof(BinT), MASK = (1u << BITS) - 1u;
     const unsigned q = blockIdx.y;
-    const unsigned short *b = bins + (size_t)q * S_local;
+    const BinT *b = bins + (size_t)q * S_local;
     unsigned *hq = hist + (size_t)q * NB;
     if (use_smem) {
         for (unsigned i = threadIdx.x; i < NB; i += blockDim.x) hs[i] = 0;
@@ -613,22 +630,23 @@ __global__ void __launch_bounds__(256) k_big_hist(const unsigned short *__restri
         if (use_smem) atomicAdd(&hs[v], n);
         else atomicAdd(&hq[v], n);
     };
-    // eight bins per 128-bit load; equal neighbours (the scores of a query concentrate in a few bins) share one atomic
-    const bool vec = (S_local % 8 == 0) && ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
-    const unsigned long long n8 = vec ? S_local / 8 : 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (unsigned long long)gridDim.x * blockDim.x) {
+    // one 128-bit load per thread and iteration; equal neighbours (the scores of a query concentrate in a few bins) share
+    // one atomic
+    const bool vec = (S_local % PER == 0) && ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    const unsigned long long nv = vec ? S_local / PER : 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(b) + i);
         const unsigned w[4] = {v4.x, v4.y, v4.z, v4.w};
-        unsigned cur = w[0] & 0xFFFFu, cnt = 0;
+        unsigned cur = w[0] & MASK, cnt = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const unsigned v = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+        for (unsigned k = 0; k < PER; k++) {
+            const unsigned v = (w[k * BITS / 32] >> ((k * BITS) % 32)) & MASK;
             if (v != cur) { add(cur, cnt); cur = v; cnt = 0; }
             cnt++;
         }
         add(cur, cnt);
     }
-    for (unsigned long long i = n8 * 8 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < S_local; i += (unsigned long long)gridDim.x * blockDim.x)
+    for (unsigned long long i = nv * PER + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < S_local; i += (unsigned long long)gridDim.x * blockDim.x)
         add((unsigned)b[i], 1u);
     if (use_smem) {
         __syncthreads();
@@ -725,7 +743,7 @@ __global__ void __launch_bounds__(SOFTMAX_RANGES) k_big_softmax(const SoftmaxPar
 // -2^iwl edge); thr[] = lowest bin with a non-zero code skips the table lookup for almost every slot.
 // -------------------------------------------------------------------------------------------------
 struct ReadParams {
-    const unsigned short *bins;
+    const void *bins;
     const unsigned char *pq;
     const unsigned *thr;
     const signed char *C;
@@ -736,35 +754,77 @@ struct ReadParams {
     unsigned *nsel;             // optional [Q]: number of selected slots (diagnostics)
 };
 
+template <typename BinT>
 __global__ void __launch_bounds__(256) k_big_read(const ReadParams p)
 {
+    constexpr unsigned PER = 16 / sizeof(BinT);              // bins per 128-bit load
+    constexpr unsigned BITS = 8 * sizeof(BinT), MASK = (1u << BITS) - 1u;
     const unsigned q = blockIdx.y, lane = threadIdx.x & 31;
-    const unsigned short *b = p.bins + (size_t)q * p.S_local;
+    const BinT *b = reinterpret_cast<const BinT *>(p.bins) + (size_t)q * p.S_local;
     const unsigned char *pq = p.pq + (size_t)q * p.NB;
     const unsigned thr = p.thr[q];
     if (thr >= p.NB) return;
+    // the selected slots of one query are at most 2^frac: every lane scans PER bins per 128-bit load, rejects them with
+    // one packed compare per word when the bins are bytes, and the warp gathers the C row of each (rare) hit together
+    const bool vec = (p.S_local % PER == 0) && ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    const unsigned long long n_items = vec ? p.S_local / PER : p.S_local;      // work items: vectors or single bins
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long n_iter = (p.S_local + stride - 1) / stride;
+    const unsigned long long n_iter = (n_items + stride - 1) / stride;
+    // byte compare v >= thr on four packed bytes: high bit of ((v & 0x7F) + K) combined with the byte's own high bit
+    const unsigned K = (thr <= 128u) ? (128u - thr) * 0x01010101u : (256u - thr) * 0x01010101u;
     for (unsigned long long it = 0; it < n_iter; it++) {
         const unsigned long long i = it * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-        unsigned code = 0;
-        if (i < p.S_local) {
-            const unsigned v = b[i];
-            if (v >= thr) code = pq[v];                       // thr = lowest bin whose code is non-zero
-        }
-        unsigned hits = __ballot_sync(0xffffffffu, code != 0u);
-        while (hits) {
-            const unsigned src = (unsigned)(__ffs((int)hits) - 1);
-            hits &= hits - 1u;
-            const unsigned long long slot = __shfl_sync(0xffffffffu, i, src);
-            const int pc = (int)__shfl_sync(0xffffffffu, code, src);
-            const signed char *crow = p.C + slot * p.d;
-            for (unsigned c = lane; c < p.d; c += 32) {
-                const int c_f = qi_requant((int)crow[c], p.f.fw, p.f.lf, p.f.ff);
-                const int term = qi_mul(pc, c_f, p.f.lf, p.f.ff);
-                if (term) atomicAdd(&p.partial[(size_t)q * p.d + c], term);
+        unsigned w[4] = {0u, 0u, 0u, 0u};
+        unsigned hitmask = 0;                                 // bit k: bin k of this item is selected
+        if (i < n_items) {
+            if (vec) {
+                const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(b) + i);
+                w[0] = v4.x; w[1] = v4.y; w[2] = v4.z; w[3] = v4.w;
+                bool maybe = true;
+                if (sizeof(BinT) == 1) {
+                    unsigned any = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const unsigned lo = (w[k] & 0x7F7F7F7Fu) + K;
+                        any |= (thr <= 128u) ? (lo | w[k]) : (lo & w[k]);
+                    }
+                    maybe = (any & 0x80808080u) != 0u;
+                }
+                if (maybe) {
+#pragma unroll
+                    for (unsigned k = 0; k < PER; k++) {
+                        const unsigned v = (w[k * BITS / 32] >> ((k * BITS) % 32)) & MASK;
+                        if (v >= thr && pq[v]) hitmask |= 1u << k;
+                    }
+                }
+            } else {
+                w[0] = (unsigned)b[i];
+                if (w[0] >= thr && pq[w[0]]) hitmask = 1u;
             }
-            if (p.nsel && lane == 0) atomicAdd(&p.nsel[q], 1u);
+        }
+        unsigned lanes = __ballot_sync(0xffffffffu, hitmask != 0u);
+        while (lanes) {
+            const unsigned src = (unsigned)(__ffs((int)lanes) - 1);
+            lanes &= lanes - 1u;
+            unsigned hm = __shfl_sync(0xffffffffu, hitmask, src);
+            const unsigned long long item = __shfl_sync(0xffffffffu, i, src);
+            while (hm) {
+                const unsigned k = (unsigned)(__ffs((int)hm) - 1);
+                hm &= hm - 1u;
+                // the bin value sits in the source lane's registers
+                const unsigned wi = k * BITS / 32;            // warp-uniform
+                const unsigned word = __shfl_sync(0xffffffffu, wi == 0 ? w[0] : (wi == 1 ? w[1] : (wi == 2 ? w[2] : w[3])), src);
+                const unsigned v = (word >> ((k * BITS) % 32)) & MASK;
+                const int pc = (int)pq[v];
+                const unsigned long long slot = vec ? item * PER + k : item;
+                const signed char *crow = p.C + slot * p.d;
+                for (unsigned c = lane; c < p.d; c += 32) {
+                    const int c_f = qi_requant((int)crow[c], p.f.fw, p.f.lf, p.f.ff);
+                    const int term = qi_mul(pc, c_f, p.f.lf, p.f.ff);
+                    if (term) atomicAdd(&p.partial[(size_t)q * p.d + c], term);
+                }
+                if (p.nsel && lane == 0) atomicAdd(&p.nsel[q], 1u);
+            }
         }
     }
 }
@@ -909,7 +969,8 @@ struct qmann_bigmem {
     signed char *Y_own[MAXH];
     unsigned char *rowmax[MAXH];
     bool fast[MAXH];
-    unsigned short *bins;            // [Q_max][S_local]
+    void *bins;                      // [Q_max][S_local] uint8 (mode 2) or uint16 (mode 3)
+    int bin8;
     unsigned char *pq;               // [Q_max][NB]
     unsigned *thr, *nsel;
     float *zbuf;
@@ -1033,7 +1094,8 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
                     !(env_mma && atoi(env_mma) == 0);
         if (b->mma_ok) BCUDA(cudaMalloc((void **)&b->bfrag, (size_t)((Q_max + MMA_QB - 1) / MMA_QB) * frag_bytes));
     }
-    BCUDA(cudaMalloc((void **)&b->bins, std::max<size_t>(2, (size_t)Q_max * S_local * 2)));
+    b->bin8 = (b->NB <= 256) ? 1 : 0;                                  // mode 2: 2*127+1 bins fit a byte
+    BCUDA(cudaMalloc((void **)&b->bins, std::max<size_t>(16, (size_t)Q_max * S_local * (b->bin8 ? 1 : 2))));
     BCUDA(cudaMalloc((void **)&b->pq, (size_t)Q_max * b->NB));
     BCUDA(cudaMalloc((void **)&b->thr, (size_t)Q_max * 4));
     BCUDA(cudaMalloc((void **)&b->nsel, (size_t)Q_max * 4));
@@ -1120,7 +1182,7 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
     if (b->S_local) {
         ScoreParams sp;
         sp.M = b->M[h]; sp.S_local = b->S_local; sp.d = d; sp.Q = Q; sp.f = f; sp.const_scale = b->cfg.const_scale;
-        sp.ub = b->ub; sp.av = b->av; sp.sv = b->sv; sp.bins = b->bins;
+        sp.ub = b->ub; sp.av = b->av; sp.sv = b->sv; sp.bins = b->bins; sp.bin8 = b->bin8;
         sp.bias = (b->cfg.mode == 3) ? b->bias : (unsigned)f.la;
         int rc;
         const bool prof = b->profile && b->pused + 2 <= 2 * MAXH;
@@ -1132,7 +1194,7 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
             count_launch();
             MmaScoreParams mp;
             mp.Y = b->Y[h]; mp.rowmax = b->rowmax[h]; mp.S_local = b->S_local; mp.d = d; mp.Q = Q; mp.la = f.la; mp.fb = f.fb;
-            mp.ub8 = b->ub8; mp.umax = b->umax; mp.bfrag = b->bfrag; mp.bins = b->bins; mp.bias = (unsigned)f.la;
+            mp.ub8 = b->ub8; mp.umax = b->umax; mp.bfrag = b->bfrag; mp.bins = b->bins; mp.bin8 = b->bin8; mp.bias = (unsigned)f.la;
             const size_t smem = (size_t)frag_vec * 16 + MMA_QB * 4;
             BCUDA(cudaFuncSetAttribute(k_big_scores_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned long long tiles = (b->S_local + 15) / 16;
@@ -1145,7 +1207,7 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
         else if (b->fast[h]) {
             FastScoreParams fp;
             fp.Y = b->Y[h]; fp.rowmax = b->rowmax[h]; fp.S_local = b->S_local; fp.d = d; fp.Q = Q; fp.la = f.la; fp.fb = f.fb;
-            fp.ub8 = b->ub8; fp.umax = b->umax; fp.bins = b->bins; fp.bias = (unsigned)f.la;
+            fp.ub8 = b->ub8; fp.umax = b->umax; fp.bins = b->bins; fp.bin8 = b->bin8; fp.bias = (unsigned)f.la;
             rc = dispatch_scores_fast(b, fp, st);
         }
         else if (b->cfg.mode == 3) rc = (Q >= 4) ? launch_scores<3, 4>(b, sp, st) : launch_scores<3, 1>(b, sp, st);
@@ -1155,7 +1217,8 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
         // mode 2 bins are code + la of THIS hop; the histogram is indexed with the common bias
         const int use_smem = b->NB <= 8192;
         const unsigned gx = (unsigned)std::min<unsigned long long>((b->S_local + 255) / 256, (unsigned long long)b->sm_count * 4);
-        k_big_hist<<<dim3(std::max(1u, gx), Q), 256, use_smem ? b->NB * 4 : 0, st>>>(b->bins, b->S_local, b->NB, dev_hist, use_smem);
+        if (b->bin8) k_big_hist<unsigned char><<<dim3(std::max(1u, gx), Q), 256, use_smem ? b->NB * 4 : 0, st>>>(reinterpret_cast<const unsigned char *>(b->bins), b->S_local, b->NB, dev_hist, use_smem);
+        else         k_big_hist<unsigned short><<<dim3(std::max(1u, gx), Q), 256, use_smem ? b->NB * 4 : 0, st>>>(reinterpret_cast<const unsigned short *>(b->bins), b->S_local, b->NB, dev_hist, use_smem);
         count_launch();
         BCUDA(cudaPeekAtLastError());
     }
@@ -1181,8 +1244,9 @@ int qmann_bigmem_hop_read(qmann_bigmem *b, uint32_t h, const uint32_t *dev_hist,
         ReadParams rp;
         rp.bins = b->bins; rp.pq = b->pq; rp.thr = b->thr; rp.C = b->C[h]; rp.S_local = b->S_local; rp.NB = b->NB; rp.d = d; rp.f = f;
         rp.partial = dev_partial; rp.nsel = b->nsel;
-        const unsigned gx = (unsigned)std::min<unsigned long long>((b->S_local + 255) / 256, (unsigned long long)b->sm_count * 4);
-        k_big_read<<<dim3(std::max(1u, gx), Q), 256, 0, st>>>(rp);
+        const unsigned gx = (unsigned)std::min<unsigned long long>((b->S_local / 8 + 255) / 256 + 1, (unsigned long long)b->sm_count * 4);
+        if (b->bin8) k_big_read<unsigned char><<<dim3(std::max(1u, gx), Q), 256, 0, st>>>(rp);
+        else         k_big_read<unsigned short><<<dim3(std::max(1u, gx), Q), 256, 0, st>>>(rp);
         count_launch();
     }
     BCUDA(cudaPeekAtLastError());
