@@ -439,15 +439,6 @@ __device__ __forceinline__ void indicator_planes(unsigned yw, unsigned &i1, unsi
     i3 = ((a0 & a1) * 0xFFu) & sg;
 }
 
-// some product of this (row, query) may saturate: the reference order of operations, product by product
-__device__ __noinline__ int exact_row_score(const signed char *__restrict__ yr, const signed char *__restrict__ ur, unsigned d, int la, int fb)
-{
-    int sp = 0;
-#pragma unroll 1
-    for (unsigned t = 0; t < d; t++) sp += qi_mul((int)yr[t], (int)ur[t], la, fb);
-    return sp;
-}
-
 __global__ void __launch_bounds__(256, 2) k_big_scores_mma(const MmaScoreParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
@@ -528,8 +519,13 @@ __global__ void __launch_bounds__(256, 2) k_big_scores_mma(const MmaScoreParams 
                 const unsigned long long row = hi ? rowB : rowA;
                 if (q >= p.Q || !(hi ? okB : okA)) continue;
                 int tot = acc[nt][j] >> 2;                           // exact: the accumulator is a multiple of 4
-                if ((hi ? rmB : rmA) * umax_s[ql] > sat_lim)
-                    tot = exact_row_score(p.Y + row * d, p.ub8 + (size_t)q * d, d, la, p.fb);    // rare: kept out of line
+                if ((hi ? rmB : rmA) * umax_s[ql] > sat_lim) {
+                    // some product of this (row, query) may saturate: the reference order of operations
+                    const signed char *yr = p.Y + row * d, *ur = p.ub8 + (size_t)q * d;
+                    int sp = 0;
+                    for (unsigned t = 0; t < d; t++) sp += qi_mul((int)yr[t], (int)ur[t], la, p.fb);
+                    tot = sp;
+                }
                 store_bin(p.bins, p.bin8, (size_t)q * p.S_local + row, (unsigned)(qi_clamp(tot, la) + (int)p.bias));
             }
         }

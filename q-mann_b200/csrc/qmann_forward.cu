@@ -93,6 +93,9 @@ struct qmann_model {
     size_t e2e_m_cap = 0, e2e_n_cap = 0;
     cudaStream_t e2e_compute = nullptr, e2e_copy = nullptr;
     std::vector<cudaEvent_t> e2e_events;
+    // sentence offsets of the host entries (grow-only device buffer, no allocation per call)
+    qmann_batch *host_batch = nullptr;
+    size_t host_batch_cap = 0;
     // qmann_infer_ids_host staging (grow-only)
     uint16_t *ids_dev = nullptr;
     uint32_t *rowoff_dev = nullptr, *ans_dev = nullptr, *e2e_pred2 = nullptr;
@@ -390,6 +393,7 @@ void qmann_model_destroy(qmann_model *m)
     if (!m) return;
     cudaFree(m->dev_img); cudaFree(m->dev_lut); cudaFree(m->dev_rec); cudaFree(m->dev_heap); cudaFree(m->dev_heap_used);
     cudaFree(m->dev_slow_list); cudaFree(m->dev_slow_list2); cudaFree(m->dev_img_swar); cudaFree(m->dev_err); cudaFree(m->dev_colmax);
+    if (m->host_batch) qmann_batch_destroy(m->host_batch);
     cudaFree(m->ids_dev); cudaFree(m->rowoff_dev); cudaFree(m->ans_dev); cudaFree(m->e2e_pred2); cudaFree(m->e2e_h2);
     cudaFree(m->e2e_m); cudaFree(m->e2e_q); cudaFree(m->e2e_a); cudaFree(m->e2e_h); cudaFree(m->e2e_pred); cudaFree(m->e2e_match);
     if (m->e2e_compute) cudaStreamDestroy(m->e2e_compute);
@@ -425,6 +429,31 @@ void qmann_batch_destroy(qmann_batch *b)
     if (!b) return;
     cudaFree(b->dev_sen_off);
     delete b;
+}
+
+// Batch descriptor of the host entries: owned by the model, its device buffer only grows, the offsets are uploaded on
+// `st` (the copy stream, ahead of the first chunk).
+static int host_batch_prepare(qmann_model *m, const uint32_t *n_sen, uint32_t N, cudaStream_t st, qmann_batch **out)
+{
+    if (!m->host_batch) { m->host_batch = new qmann_batch(); m->host_batch->dev_sen_off = nullptr; }
+    qmann_batch *b = m->host_batch;
+    b->N = N;
+    b->sen_off.resize((size_t)N + 1);
+    b->sen_off[0] = 0;
+    b->max_sen = 0;
+    for (uint32_t i = 0; i < N; i++) {
+        b->sen_off[i + 1] = b->sen_off[i] + n_sen[i];
+        b->max_sen = std::max(b->max_sen, n_sen[i]);
+    }
+    b->sum_sen = b->sen_off[N];
+    if ((size_t)N + 1 > m->host_batch_cap) {
+        cudaFree(b->dev_sen_off); b->dev_sen_off = nullptr; m->host_batch_cap = 0;
+        QCUDA(cudaMalloc((void **)&b->dev_sen_off, ((size_t)N + 1) * sizeof(unsigned long long)));
+        m->host_batch_cap = (size_t)N + 1;
+    }
+    QCUDA(cudaMemcpyAsync(b->dev_sen_off, b->sen_off.data(), ((size_t)N + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    *out = b;
+    return QMANN_OK;
 }
 
 // The two input formats of a batch: the dense fp32 arenas (the reference's boundary, compacted by k_compact) or the
@@ -553,12 +582,14 @@ int qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, c
                      uint32_t *pred_host, uint32_t *match, float *cost)
 {
     if (!m || !q_host || !n_sen || !pred_host) return fail(QMANN_E_ARG, "null argument");
+#define QC2(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail(QMANN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } while (0)
+    if (!m->e2e_compute) QC2(cudaStreamCreateWithFlags(&m->e2e_compute, cudaStreamNonBlocking));
+    if (!m->e2e_copy) QC2(cudaStreamCreateWithFlags(&m->e2e_copy, cudaStreamNonBlocking));
     qmann_batch *b = nullptr;
-    int rc = qmann_batch_create(&b, n_sen, N);
+    int rc = host_batch_prepare(m, n_sen, N, m->e2e_copy, &b);
     if (rc) return rc;
-    if (b->max_sen > m->cfg.S_max) { qmann_batch_destroy(b); return fail(QMANN_E_ARG, "a story has more sentences than S_max"); }
+    if (b->max_sen > m->cfg.S_max) return fail(QMANN_E_ARG, "a story has more sentences than S_max");
     const size_t V = m->cfg.V;
-#define QC2(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { qmann_batch_destroy(b); return fail(QMANN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
     // grow-only device arenas owned by the model: repeated calls reuse them
     if (b->sum_sen > m->e2e_m_cap) {
         cudaFree(m->e2e_m); m->e2e_m = nullptr; m->e2e_m_cap = 0;
@@ -601,7 +632,7 @@ int qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, c
         FwdInput in;
         in.dev_m = dm; in.dev_q = dq; in.dev_a = da;
         rc = forward_range(m, b, s0, n, in, m->e2e_pred, dh, da ? m->e2e_match : nullptr, nullptr, sc);
-        if (rc) { qmann_batch_destroy(b); return rc; }
+        if (rc) return rc;
     }
     QC2(cudaMemcpyAsync(pred_host, m->e2e_pred, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
     uint32_t mt = 0;
@@ -612,7 +643,6 @@ int qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, c
     QC2(cudaMemcpyAsync(&err, m->dev_err, sizeof(unsigned), cudaMemcpyDeviceToHost, sc));
     QC2(cudaStreamSynchronize(sc));
 #undef QC2
-    qmann_batch_destroy(b);
     if (match) *match = mt;
     if (cost && dh) {
         // the reference accumulates cost += -h[y] story by story in fp32 (layer_cuda.cu:2198)
@@ -629,11 +659,13 @@ int qmann_infer_ids_host(qmann_model *m, const uint16_t *ids_host, const uint32_
 {
     if (!m || !ids_host || !row_off_host || !n_sen || !pred_host) return fail(QMANN_E_ARG, "null argument");
     if (m->cfg.V > 65535u) return fail(QMANN_E_ARG, "ids are 16-bit");
+#define QC2(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail(QMANN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } while (0)
+    if (!m->e2e_compute) QC2(cudaStreamCreateWithFlags(&m->e2e_compute, cudaStreamNonBlocking));
+    if (!m->e2e_copy) QC2(cudaStreamCreateWithFlags(&m->e2e_copy, cudaStreamNonBlocking));
     qmann_batch *b = nullptr;
-    int rc = qmann_batch_create(&b, n_sen, N);
+    int rc = host_batch_prepare(m, n_sen, N, m->e2e_copy, &b);
     if (rc) return rc;
-    if (b->max_sen > m->cfg.S_max) { qmann_batch_destroy(b); return fail(QMANN_E_ARG, "a story has more sentences than S_max"); }
-#define QC2(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { qmann_batch_destroy(b); return fail(QMANN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    if (b->max_sen > m->cfg.S_max) return fail(QMANN_E_ARG, "a story has more sentences than S_max");
     const size_t R = (size_t)N + b->sum_sen;                 // rows: one question and n_sen sentences per story
     const size_t n_ids = row_off_host[R];
     if (n_ids > m->ids_cap) {
@@ -681,7 +713,7 @@ int qmann_infer_ids_host(qmann_model *m, const uint16_t *ids_host, const uint32_
         FwdInput in;
         in.dev_ids = m->ids_dev; in.dev_row_off = m->rowoff_dev; in.dev_ans = ans_host ? m->ans_dev : nullptr;
         rc = forward_range(m, b, s0, n, in, m->e2e_pred2, dh, ans_host ? m->e2e_match : nullptr, nullptr, sc);
-        if (rc) { qmann_batch_destroy(b); return rc; }
+        if (rc) return rc;
     }
     QC2(cudaMemcpyAsync(pred_host, m->e2e_pred2, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
     uint32_t mt = 0;
@@ -693,7 +725,6 @@ int qmann_infer_ids_host(qmann_model *m, const uint16_t *ids_host, const uint32_
     QC2(cudaStreamSynchronize(sc));
     if (err) QC2(cudaMemset(m->dev_err, 0, sizeof(unsigned)));
 #undef QC2
-    qmann_batch_destroy(b);
     if (match) *match = mt;
     if (cost && dh) {
         float cacc = *cost;

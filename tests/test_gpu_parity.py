@@ -253,3 +253,30 @@ def test_shim_layers_match_reference_library_live(qmann):
         o = torch.zeros(d, device="cuda"); L.cuda_sum_vec_fwd(u.data_ptr(), M[0].contiguous().data_ptr(), o.data_ptr(), d, True, 5, 2, 3, False); return o
     for fn in (dense, dense_f, dense_mat, score, read, appx, softmax, sumv):
         both(fn)
+
+
+@pytest.mark.parametrize("preset,sigma", [("C2", 0.5), ("C2", 1.3), ("C4", 0.7), ("C1", 2.5)])
+def test_packed_path_equals_unpacked_and_instrumented(preset, sigma, qmann, synth, monkeypatch):
+    """Production kernels, three ways: packed embedding + scorer (k_forward_fast<.., 2, true>: stories whose rows are
+    narrow, the rest falls through), packed path switched off (QMANN_SWAR=0), and the instrumented general kernel.
+    Same predictions and match counts on 3000 ragged stories; sigma 1.3 mixes narrow and non-narrow stories, 2.5 has
+    none that is narrow."""
+    import torch
+    cfg = synth.preset_config(preset)
+    w = synth.make_weights(cfg, 41, sigma=sigma)
+    st = synth.make_stories(cfg, 3000, 42, S=min(cfg.S_max, 50), ragged=True)
+    res = {}
+    for tag, env in (("packed", "1"), ("unpacked", "0")):
+        monkeypatch.setenv("QMANN_SWAR", env)
+        model = qmann.lib.Model(cfg, w)
+        db = model.upload(st)
+        out = model.forward(db, with_answers=True, want_h=False, debug=False)
+        torch.cuda.synchronize()
+        res[tag] = (out["pred"].cpu().numpy()[:st.N].copy(), int(out["match"].cpu().numpy()[0]))
+        if tag == "packed":
+            dbg = model.forward(db, with_answers=True, want_h=True, debug=True)
+            torch.cuda.synchronize()
+            res["general"] = (dbg["pred"].cpu().numpy()[:st.N].copy(), int(dbg["match"].cpu().numpy()[0]))
+    for tag in ("unpacked", "general"):
+        np.testing.assert_array_equal(res["packed"][0], res[tag][0], err_msg=tag)
+        assert res["packed"][1] == res[tag][1]
