@@ -439,7 +439,21 @@ __device__ __forceinline__ void indicator_planes(unsigned yw, unsigned &i1, unsi
     i3 = ((a0 & a1) * 0xFFu) & sg;
 }
 
-__global__ void __launch_bounds__(256, 2) k_big_scores_mma(const MmaScoreParams p)
+// 16-byte asynchronous copy global -> shared (zero-fill when !valid)
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *gptr, bool valid)
+{
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Shared memory: [query planes, d*256 B][umax, 256 B][per warp: two tile buffers of 16 rows x d bytes].
+// A warp streams its tiles through the two buffers with cp.async (the copy of tile i+1 runs under the 256 IMMAs of tile
+// i; no staging registers), rows are stored with their 16-byte chunks XOR-swizzled by the row parity (chunk ^ 4 for odd
+// rows) so that the quarter-warp reads of two neighbouring rows hit disjoint banks.
+__global__ void __launch_bounds__(512, 1) k_big_scores_mma(const MmaScoreParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -449,6 +463,7 @@ __global__ void __launch_bounds__(256, 2) k_big_scores_mma(const MmaScoreParams 
     const unsigned frag_vec = KS * 8 * 2 * 32;             // uint4 per query block
     uint4 *bs = reinterpret_cast<uint4 *>(sm);
     unsigned *umax_s = reinterpret_cast<unsigned *>(sm + (size_t)frag_vec * 16);
+    unsigned char *tile0 = sm + (size_t)frag_vec * 16 + 256 + (size_t)wid * 2 * 16 * d;
     {
         const uint4 *src = p.bfrag + (size_t)blockIdx.y * frag_vec;
         for (unsigned i = threadIdx.x; i < frag_vec; i += blockDim.x) bs[i] = src[i];
@@ -458,7 +473,30 @@ __global__ void __launch_bounds__(256, 2) k_big_scores_mma(const MmaScoreParams 
     const int la = p.la;
     const unsigned sat_lim = 4u * (unsigned)la + 3u;
     const unsigned long long n_tiles = (p.S_local + 15) / 16;
-    for (unsigned long long tix = (unsigned long long)blockIdx.x * nw + wid; tix < n_tiles; tix += (unsigned long long)gridDim.x * nw) {
+    const unsigned long long tstride = (unsigned long long)gridDim.x * nw;
+    const unsigned c16 = d / 16;                            // 16-byte chunks per row
+    const unsigned swz_bit = ((c16 & 7u) == 0u) ? 4u : 0u;  // chunk ^ 4 on odd rows needs rows of whole 8-chunk groups (d % 128 == 0)
+    const unsigned tile_smem0 = (unsigned)__cvta_generic_to_shared(tile0);
+
+    // asynchronous copy of tile `tix` into buffer `buf`: 16 rows x c16 chunks, lanes over consecutive chunks (coalesced)
+    auto stage = [&](unsigned long long tix, unsigned buf) {
+        const unsigned base = tile_smem0 + buf * 16u * d;
+        for (unsigned i = lane; i < 16u * c16; i += 32) {
+            const unsigned r = i / c16, j = i % c16;
+            const unsigned long long row = tix * 16 + r;
+            const bool ok = row < p.S_local;
+            cp_async16(base + r * d + 16u * (j ^ ((r & 1u) * swz_bit)), p.Y + (ok ? row : 0ull) * d + 16u * j, ok);
+        }
+        cp_async_commit();
+    };
+
+    unsigned long long tix = (unsigned long long)blockIdx.x * nw + wid;
+    unsigned buf = 0;
+    if (tix < n_tiles) stage(tix, 0);
+    for (; tix < n_tiles; tix += tstride, buf ^= 1u) {
+        if (tix + tstride < n_tiles) { stage(tix + tstride, buf ^ 1u); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();
         const unsigned long long rowA = tix * 16 + g, rowB = rowA + 8;
         const bool okA = rowA < p.S_local, okB = rowB < p.S_local;
         int acc[8][4];
@@ -466,49 +504,38 @@ __global__ void __launch_bounds__(256, 2) k_big_scores_mma(const MmaScoreParams 
         for (int nt = 0; nt < 8; nt++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[nt][j] = 0;
-        const signed char *pa = p.Y + rowA * d + 16u * c, *pb = p.Y + rowB * d + 16u * c;
+        const unsigned char *ta = tile0 + (size_t)buf * 16 * d + (size_t)g * d;          // row g; row g+8 has the same parity
+        const unsigned swz = (g & 1u) * swz_bit;
 #pragma unroll 1
-        for (unsigned kk0 = 0; kk0 < d / 64; kk0 += 2) {
-            // two 64-byte steps (four k-steps) per iteration: four 128-bit loads in flight per lane
-            uint4 ya[2], yb[2];
+        for (unsigned kk = 0; kk < d / 64; kk++) {
+            const unsigned off = 16u * ((4u * kk + c) ^ swz);
+            const uint4 ya = *reinterpret_cast<const uint4 *>(ta + off);
+            const uint4 yb = *reinterpret_cast<const uint4 *>(ta + 8u * d + off);
+            const unsigned wa[4] = {ya.x, ya.y, ya.z, ya.w};
+            const unsigned wb[4] = {yb.x, yb.y, yb.z, yb.w};
 #pragma unroll
-            for (int s2 = 0; s2 < 2; s2++) {
-                const unsigned kk = kk0 + s2;
-                ya[s2] = make_uint4(0u, 0u, 0u, 0u);
-                yb[s2] = make_uint4(0u, 0u, 0u, 0u);
-                if (kk < d / 64) {
-                    if (okA) ya[s2] = ldg_stream(pa + 64u * kk);
-                    if (okB) yb[s2] = ldg_stream(pb + 64u * kk);
-                }
-            }
+            for (int odd = 0; odd < 2; odd++) {
+                // A fragments of this k-step: a0/a2 from row g (words 2 odd, 2 odd + 1), a1/a3 from row g + 8
+                unsigned A[4][4];
+                A[0][0] = wa[2 * odd]; A[0][2] = wa[2 * odd + 1]; A[0][1] = wb[2 * odd]; A[0][3] = wb[2 * odd + 1];
 #pragma unroll
-            for (int s2 = 0; s2 < 2; s2++) {
-                const unsigned kk = kk0 + s2;
-                if (kk >= d / 64) break;
-                const unsigned wa[4] = {ya[s2].x, ya[s2].y, ya[s2].z, ya[s2].w};
-                const unsigned wb[4] = {yb[s2].x, yb[s2].y, yb[s2].z, yb[s2].w};
+                for (int j = 0; j < 4; j++) indicator_planes(A[0][j], A[1][j], A[2][j], A[3][j]);
+                const unsigned ks = 2 * kk + odd;
+                const uint4 *bk = bs + (size_t)ks * (8 * 2 * 32) + lane;
 #pragma unroll
-                for (int odd = 0; odd < 2; odd++) {
-                    // A fragments of this k-step: a0/a2 from row g (words 2 odd, 2 odd + 1), a1/a3 from row g + 8
-                    unsigned A[4][4];
-                    A[0][0] = wa[2 * odd]; A[0][2] = wa[2 * odd + 1]; A[0][1] = wb[2 * odd]; A[0][3] = wb[2 * odd + 1];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) indicator_planes(A[0][j], A[1][j], A[2][j], A[3][j]);
-                    const unsigned ks = 2 * kk + odd;
-                    const uint4 *bk = bs + (size_t)ks * (8 * 2 * 32) + lane;
-#pragma unroll
-                    for (int nt = 0; nt < 8; nt++) {
-                        const uint4 b01 = bk[nt * 64], b23 = bk[nt * 64 + 32];
-                        mma_s8(acc[nt], A[0][0], A[0][1], A[0][2], A[0][3], b01.x, b01.y);
-                        mma_s8(acc[nt], A[1][0], A[1][1], A[1][2], A[1][3], b01.z, b01.w);
-                        mma_s8(acc[nt], A[2][0], A[2][1], A[2][2], A[2][3], b23.x, b23.y);
-                        mma_s8(acc[nt], A[3][0], A[3][1], A[3][2], A[3][3], b23.z, b23.w);
-                    }
+                for (int nt = 0; nt < 8; nt++) {
+                    const uint4 b01 = bk[nt * 64], b23 = bk[nt * 64 + 32];
+                    mma_s8(acc[nt], A[0][0], A[0][1], A[0][2], A[0][3], b01.x, b01.y);
+                    mma_s8(acc[nt], A[1][0], A[1][1], A[1][2], A[1][3], b01.z, b01.w);
+                    mma_s8(acc[nt], A[2][0], A[2][1], A[2][2], A[2][3], b23.x, b23.y);
+                    mma_s8(acc[nt], A[3][0], A[3][1], A[3][2], A[3][3], b23.z, b23.w);
                 }
             }
         }
-        // epilogue: C fragment (row g | g+8, query nt*8 + 2c | +1)
+        __syncwarp();                                        // every lane is done with this buffer before it is refilled
+        // epilogue: C fragment (row g | g+8, query nt*8 + 2c | +1); entries whose products may saturate are only marked
         const unsigned rmA = okA ? (unsigned)p.rowmax[rowA] : 0u, rmB = okB ? (unsigned)p.rowmax[rowB] : 0u;
+        unsigned risky = 0;                                  // bit 4 nt + j
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
 #pragma unroll
@@ -516,18 +543,24 @@ __global__ void __launch_bounds__(256, 2) k_big_scores_mma(const MmaScoreParams 
                 const unsigned ql = nt * 8 + 2 * c + (j & 1);
                 const unsigned q = q0 + ql;
                 const bool hi = j >= 2;
-                const unsigned long long row = hi ? rowB : rowA;
                 if (q >= p.Q || !(hi ? okB : okA)) continue;
-                int tot = acc[nt][j] >> 2;                           // exact: the accumulator is a multiple of 4
-                if ((hi ? rmB : rmA) * umax_s[ql] > sat_lim) {
-                    // some product of this (row, query) may saturate: the reference order of operations
-                    const signed char *yr = p.Y + row * d, *ur = p.ub8 + (size_t)q * d;
-                    int sp = 0;
-                    for (unsigned t = 0; t < d; t++) sp += qi_mul((int)yr[t], (int)ur[t], la, p.fb);
-                    tot = sp;
-                }
-                store_bin(p.bins, p.bin8, (size_t)q * p.S_local + row, (unsigned)(qi_clamp(tot, la) + (int)p.bias));
+                if ((hi ? rmB : rmA) * umax_s[ql] > sat_lim) { risky |= 1u << (4 * nt + j); continue; }
+                store_bin(p.bins, p.bin8, (size_t)q * p.S_local + (hi ? rowB : rowA),
+                          (unsigned)(qi_clamp(acc[nt][j] >> 2, la) + (int)p.bias));          // exact: a multiple of 4
             }
+        }
+        while (risky) {
+            // some product of this (row, query) may saturate: the reference order of operations, product by product
+            const unsigned k = (unsigned)(__ffs((int)risky) - 1);
+            risky &= risky - 1u;
+            const unsigned nt = k >> 2, j = k & 3u;
+            const unsigned q = q0 + nt * 8 + 2 * c + (j & 1u);
+            const unsigned long long row = (j >= 2) ? rowB : rowA;
+            const signed char *yr = p.Y + row * d, *ur = p.ub8 + (size_t)q * d;
+            int sp = 0;
+#pragma unroll 4
+            for (unsigned t = 0; t < d; t++) sp += qi_mul((int)yr[t], (int)ur[t], la, p.fb);
+            store_bin(p.bins, p.bin8, (size_t)q * p.S_local + row, (unsigned)(qi_clamp(sp, la) + (int)p.bias));
         }
     }
 }
@@ -1086,7 +1119,7 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
         // tensor-core scorer: d a multiple of 64 whose query planes (d * 256 bytes per block of 64 queries) fit shared memory
         const char *env_mma = getenv("QMANN_BIGMEM_MMA");
         const size_t frag_bytes = (size_t)c.d * 256;
-        b->mma_ok = c.mode == 2 && c.frac_bin == 2 && c.d % 64 == 0 && frag_bytes + 1024 <= (size_t)b->smem_optin &&
+        b->mma_ok = c.mode == 2 && c.frac_bin == 2 && c.d % 64 == 0 && frag_bytes + 256 + (size_t)2 * 2 * 16 * c.d <= (size_t)b->smem_optin &&
                     !(env_mma && atoi(env_mma) == 0);
         if (b->mma_ok) BCUDA(cudaMalloc((void **)&b->bfrag, (size_t)((Q_max + MMA_QB - 1) / MMA_QB) * frag_bytes));
     }
@@ -1191,11 +1224,15 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
             MmaScoreParams mp;
             mp.Y = b->Y[h]; mp.rowmax = b->rowmax[h]; mp.S_local = b->S_local; mp.d = d; mp.Q = Q; mp.la = f.la; mp.fb = f.fb;
             mp.ub8 = b->ub8; mp.umax = b->umax; mp.bfrag = b->bfrag; mp.bins = b->bins; mp.bin8 = b->bin8; mp.bias = (unsigned)f.la;
-            const size_t smem = (size_t)frag_vec * 16 + MMA_QB * 4;
+            // shared memory: query planes + umax + two tile buffers per warp; as many warps (<= 16) as fit
+            const size_t fixed = (size_t)frag_vec * 16 + 256, per_warp = (size_t)2 * 16 * d;
+            unsigned warps = (unsigned)std::min<size_t>(16, ((size_t)b->smem_optin - fixed) / per_warp);
+            if (warps == 0) return bfail(QMANN_E_NOMEM, "tensor-core scorer does not fit shared memory");
+            const size_t smem = fixed + (size_t)warps * per_warp;
             BCUDA(cudaFuncSetAttribute(k_big_scores_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned long long tiles = (b->S_local + 15) / 16;
-            const unsigned gx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((tiles + 7) / 8, (unsigned long long)b->sm_count * 2));
-            k_big_scores_mma<<<dim3(gx, qblocks), 256, smem, st>>>(mp);
+            const unsigned gx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((tiles + warps - 1) / warps, (unsigned long long)b->sm_count));
+            k_big_scores_mma<<<dim3(gx, qblocks), warps * 32, smem, st>>>(mp);
             count_launch();
             BCUDA(cudaPeekAtLastError());
             rc = QMANN_OK;
