@@ -197,7 +197,8 @@ def run_bigmem(args):
     pkg = ge.import_package()
     synth, qlib = pkg.synth, pkg.lib
     cfg = c5_config(synth)
-    Q = args.queries
+    Qs = [int(x) for x in str(args.queries).split(",") if x]
+    Q = max(Qs)
     W, K = max(3, args.warmup), max(1, args.steps)
     weights = synth.make_weights(cfg, 0x5EED0000 + 5, sigma=0.3)
     f = cfg.formats()
@@ -228,6 +229,19 @@ def run_bigmem(args):
         import torch.distributed as dist
         group = dist.group.WORLD
     mem = qlib.BigMemory(cfg, weights, M8, C8, C5_S, lo, Q_max=Q, device=dev, group=group, world=world)
+    u0_all = u0
+    rc = 0
+    for qi, Qn in enumerate(Qs):
+        rc |= _bigmem_measure(args, torch, qlib, synth, cfg, weights, mem, u0_all[:Qn].contiguous(), Qn, W, K, rank, world, local, dev, n_loc,
+                              cpu_wanted=(qi == 0))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return rc
+
+
+def _bigmem_measure(args, torch, qlib, synth, cfg, weights, mem, u0, Q, W, K, rank, world, local, dev, n_loc, cpu_wanted):
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -304,7 +318,7 @@ def run_bigmem(args):
         bytes_launch = n_loc * cfg.d                     # one hop's M shard, int8, read once per launch
         achieved = bytes_launch / (k_scores_ms / 1e3) / 1e9
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and cpu_wanted:
             rate, dt, slots, qs = c5_cpu_rate(synth, cfg, weights)
             cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{qs} queries x {slots} of the 2^20 slots in {dt:.1f} s (oracle/qmo_bigmem.py over qmann_oracle.c), "
@@ -336,10 +350,6 @@ def run_bigmem(args):
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
     return 0
 
 
@@ -405,7 +415,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
-    ap.add_argument("--queries", type=int, default=64, help="C5: queries per step")
+    ap.add_argument("--queries", type=str, default="64",
+                    help="C5: queries per step; a comma list (e.g. 1,64,1024) runs them one after the other on the same resident memory "
+                         "and prints one JSON line each")
     ap.add_argument("--input", default="dense", choices=["dense", "ids"],
                     help="C1-C4: dense fp32 arenas (the reference boundary format, the headline) or the word-id lists they are "
                          "built from (SURVEY 8f-1, reported separately, never mixed)")
