@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
     unsigned char *brow = ws + p.o_brow;               // SWAR: row biases [H][S_pad]
     const unsigned d = p.d, DP = p.DP, V = p.V;
     if (lane == 0) *reinterpret_cast<unsigned *>(ws + p.o_zent) = SWAR ? V * DP : V;
-    unsigned short *perm = reinterpret_cast<unsigned short *>(ws + p.o_perm);     // SWAR: rows ordered by entry count
+    unsigned short *perm = reinterpret_cast<unsigned short *>(ws + p.o_perm);     // rows ordered by entry count
     unsigned *cnt_s = reinterpret_cast<unsigned *>(ws + p.o_cnt);
     const unsigned lgDP = 31u - (unsigned)__clz((int)DP);
     int sel[4];
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
             for (unsigned r = lane; r < S + 1; r += 32) rend_s[r] = rend_g[r];
             const unsigned *ent_g = reinterpret_cast<const unsigned *>(rec + p.off_ent);
             for (unsigned k = lane; k < n_ent; k += 32) ent_s[k] = SWAR ? ent_g[k] * DP : ent_g[k];
-            if (SWAR && lane < 17) cnt_s[lane] = 0;
+            if (lane < 17) cnt_s[lane] = 0;
         }
         __syncwarp();
         if (SWAR) {
@@ -214,12 +214,14 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
                 if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = w;
                 continue;
             }
-            // Rows ordered by entry count (counting sort; narrow rows have at most 8 entries): the G rows of a pass then
-            // have nearly the same length and the gather loop does not idle on the longest one.  Only the order in
-            // which rows are embedded changes; every score is stored at its own row index.
+        }
+        {
+            // Rows ordered by entry count (counting sort, counts capped at 15): the G rows of a pass then have nearly
+            // the same length and the gather loop does not idle on the longest one.  Only the order in which rows are
+            // embedded changes; every score is stored at its own row index.
             for (unsigned r0 = 0; r0 < S; r0 += 32) {
                 const unsigned r = r0 + lane;
-                const unsigned key = (r < S) ? (unsigned)(rend_s[r + 1] - rend_s[r]) : 16u;
+                const unsigned key = (r < S) ? min((unsigned)(rend_s[r + 1] - rend_s[r]), 15u) : 16u;
                 const unsigned peers = __match_any_sync(0xffffffffu, key);
                 if (lane == (unsigned)(__ffs((int)peers) - 1)) cnt_s[key] += (unsigned)__popc(peers);
                 __syncwarp();
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
             __syncwarp();
             for (unsigned r0 = 0; r0 < S; r0 += 32) {
                 const unsigned r = r0 + lane;
-                const unsigned key = (r < S) ? (unsigned)(rend_s[r + 1] - rend_s[r]) : 16u;
+                const unsigned key = (r < S) ? min((unsigned)(rend_s[r + 1] - rend_s[r]), 15u) : 16u;
                 const unsigned peers = __match_any_sync(0xffffffffu, key);
                 const unsigned base = cnt_s[key];
                 const unsigned rank = (unsigned)__popc(peers & ((1u << lane) - 1u));
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
             } else
 #pragma unroll 1
             for (unsigned r0 = 0; r0 < S; r0 += G) {
-                const unsigned r = r0 + g;
+                const unsigned r = (r0 + g < S) ? (unsigned)perm[r0 + g] : S;
                 embed_fast<LPR, SWAR>(p, wso, lane, p.offA[h], (r < S) ? (int)(r + 1) : -1, acc, sel);
                 int part = 0;
                 if (MODE == 3 && fast3) {
