@@ -128,8 +128,8 @@ __device__ __forceinline__ int swar_score(const unsigned (&acc4)[4], unsigned Bw
     return D - (int)__dp4a(cs, SW_1, 0u) + 48;
 }
 
-template <int LPR, int MODE, bool SWAR>
-__global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__ FwdParams p)
+template <int LPR, int MODE, bool SWAR, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_forward_fast(const __grid_constant__ FwdParams p)
 {
     constexpr int G = 32 / LPR;
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -138,7 +138,12 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.img);
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (unsigned i = threadIdx.x; i < p.img_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        // this kernel's shared-memory image: everything in front of the fp32 answer weights, then their int8 image
+        // in the place of the fp32 rows (those are read from L2 for the few rows that need them)
+        for (unsigned i = threadIdx.x; i < p.offW / 16; i += blockDim.x) dst[i] = src[i];
+        const uint4 *src8 = reinterpret_cast<const uint4 *>(p.img + p.offW8);
+        uint4 *dst8 = reinterpret_cast<uint4 *>(smem + p.offW);
+        for (unsigned i = threadIdx.x; i < p.w8_bytes / 16; i += blockDim.x) dst8[i] = src8[i];
     }
     __syncthreads();
 
@@ -579,57 +584,120 @@ __global__ void __launch_bounds__(512, 1) k_forward_fast(const __grid_constant__
 
         // ---- answer projection, sequential fp32 (MemN2N.c:902-906, layer_cuda.cu:69-82), argmax on the
         //      probabilities (layer_cuda.cu:1918-1939) ----
+        // Only the rows that can hold the largest probability need their fp32 logit: z_i = sum_j fl(W_ij u_j) in index
+        // order.  With W = s (W8 + eps), |eps| <= 1/2, and u = n / 2^fu, the integer dot D_i = sum_j W8_ij n_j (IDP.4A)
+        // satisfies |z_i 2^fu / s - D_i| <= E = |n|_1 / 2 + gamma_{d+1} 127 |n|_1 (quantisation of W + fp32 rounding of
+        // the chain).  Every row whose probability can tie with the maximum has z_i >= z_max - 1e-5, hence
+        // D_i >= D_max - (2 E + 1e-5 2^fu / s): those candidates (1.4 rows on average) are computed exactly, from the
+        // fp32 rows in L2; all other rows get -inf, i.e. e = 0.  A tie among candidates, or h[y] requested, computes
+        // every row exactly.
         for (unsigned j = lane; j < DP; j += 32) ufl[j] = (j < d) ? (float)uvec[j] / (float)(1 << fu) : 0.0f;
         __syncwarp();
         const unsigned d4 = (d + 3) / 4;
-        float zmax = -INFINITY;
-#pragma unroll 1
-        for (unsigned i0 = 0; i0 < V; i0 += 128) {
-            float z[4] = {0.f, 0.f, 0.f, 0.f};
-            unsigned wrow[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) wrow[k] = p.offW + min(i0 + 32 * k + lane, V - 1) * (p.WS * 4u);
-#pragma unroll 1
+        const float *Wg = reinterpret_cast<const float *>(p.img + p.offW);
+        auto exact_z = [&](unsigned i) {
+            const float4 *wr = reinterpret_cast<const float4 *>(Wg + (size_t)i * p.WS);
+            float z = 0.0f;
+#pragma unroll 4
             for (unsigned j4 = 0; j4 < d4; j4++) {
+                const float4 ww = __ldg(wr + j4);
                 const float4 uu = *reinterpret_cast<const float4 *>(ufl + 4 * j4);
+                z = __fadd_rn(z, __fmul_rn(ww.x, uu.x));
+                z = __fadd_rn(z, __fmul_rn(ww.y, uu.y));
+                z = __fadd_rn(z, __fmul_rn(ww.z, uu.z));
+                z = __fadd_rn(z, __fmul_rn(ww.w, uu.w));
+            }
+            return z;
+        };
+        float zmax = -INFINITY;
+        unsigned n_cand = 0, cand_idx = 0;
+        bool need_full = !p.w8_ok || p.want_h;
+        if (!need_full) {
+            int n1 = 0;
+            for (unsigned j = lane; j < DP; j += 32) n1 += abs((int)uvec[j]);
+            n1 = __reduce_add_sync(0xffffffffu, n1);
+            const int T = n1 + (n1 >> 6) + p.ans_margin + 2;
+            int *zi = reinterpret_cast<int *>(zbuf);
+            const unsigned nw16 = (d + 15) / 16;
+            int Dmax = INT_MIN;
+#pragma unroll 1
+            for (unsigned i0 = 0; i0 < V; i0 += 128) {
+                int D[4] = {0, 0, 0, 0};
+                unsigned wrow[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) wrow[k] = p.offW + min(i0 + 32 * k + lane, V - 1) * p.W8S;
+#pragma unroll 1
+                for (unsigned w16 = 0; w16 < nw16; w16++) {
+                    const uint4 uu = *reinterpret_cast<const uint4 *>(uvec + 16 * w16);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint4 ww = *reinterpret_cast<const uint4 *>(smem + wrow[k] + 16u * w16);
+                        D[k] = __dp4a((int)ww.x, (int)uu.x, D[k]);
+                        D[k] = __dp4a((int)ww.y, (int)uu.y, D[k]);
+                        D[k] = __dp4a((int)ww.z, (int)uu.z, D[k]);
+                        D[k] = __dp4a((int)ww.w, (int)uu.w, D[k]);
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const float4 ww = *reinterpret_cast<const float4 *>(smem + wrow[k] + 16u * j4);
-                    z[k] = __fadd_rn(z[k], __fmul_rn(ww.x, uu.x));
-                    z[k] = __fadd_rn(z[k], __fmul_rn(ww.y, uu.y));
-                    z[k] = __fadd_rn(z[k], __fmul_rn(ww.z, uu.z));
-                    z[k] = __fadd_rn(z[k], __fmul_rn(ww.w, uu.w));
+                    const unsigned i = i0 + 32 * k + lane;
+                    if (i < V) { zi[i] = D[k]; Dmax = max(Dmax, D[k]); }
+                }
+            }
+            Dmax = __reduce_max_sync(0xffffffffu, Dmax);
+            const int thr = Dmax - T;
+#pragma unroll 1
+            for (unsigned i0 = 0; i0 < V; i0 += 32) {
+                const unsigned i = i0 + lane;
+                if (i < V) {
+                    float z = -INFINITY;
+                    if (zi[i] >= thr) z = exact_z(i);
+                    zbuf[i] = z;
+                    zmax = fmaxf(zmax, z);
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned i = i0 + 32 * k + lane;
-                if (i < V) { zbuf[i] = z[k]; zmax = fmaxf(zmax, z[k]); }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-        __syncwarp();
-        // h_i = fl(e_i / total) is monotone in e_i = __expf(z_i - max): only slots whose e is within
-        // 2^-20 of the largest can share the maximal probability; the double total is needed only to
-        // break such near-ties exactly, or when h[y] is requested.
-        unsigned n_cand = 0, cand_idx = 0;
+            for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+            __syncwarp();
 #pragma unroll 1
-        for (unsigned i0 = 0; i0 < V; i0 += 32) {
-            const unsigned i = i0 + lane;
-            bool cand = false;
-            if (i < V) {
-                const float e = __expf(zbuf[i] - zmax);
-                zbuf[i] = e;
-                cand = (e >= 0.99999905f);
+            for (unsigned i0 = 0; i0 < V; i0 += 32) {
+                const unsigned i = i0 + lane;
+                const bool cand = (i < V) && (__expf(zbuf[i] - zmax) >= 0.99999905f);
+                const unsigned b = __ballot_sync(0xffffffffu, cand);
+                if (b) { n_cand += __popc(b); cand_idx = i0 + 31 - __clz(b); }
             }
-            const unsigned b = __ballot_sync(0xffffffffu, cand);
-            if (b) { n_cand += __popc(b); cand_idx = i0 + 31 - __clz(b); }
+            need_full = n_cand > 1;                          // near-tie: the double total decides, every row exactly
+        }
+        if (need_full) {
+            zmax = -INFINITY;
+#pragma unroll 1
+            for (unsigned i0 = 0; i0 < V; i0 += 32) {
+                const unsigned i = i0 + lane;
+                if (i < V) { const float z = exact_z(i); zbuf[i] = z; zmax = fmaxf(zmax, z); }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+            __syncwarp();
+            // h_i = fl(e_i / total) is monotone in e_i = __expf(z_i - max): only slots whose e is within 2^-20 of the
+            // largest can share the maximal probability
+            n_cand = 0; cand_idx = 0;
+#pragma unroll 1
+            for (unsigned i0 = 0; i0 < V; i0 += 32) {
+                const unsigned i = i0 + lane;
+                bool cand = false;
+                if (i < V) {
+                    const float e = __expf(zbuf[i] - zmax);
+                    zbuf[i] = e;
+                    cand = (e >= 0.99999905f);
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, cand);
+                if (b) { n_cand += __popc(b); cand_idx = i0 + 31 - __clz(b); }
+            }
         }
         __syncwarp();
         unsigned pred_i = cand_idx;
         float h_true_v = 0.0f;
-        if ((n_cand > 1) || p.want_h) {
+        if (need_full && ((n_cand > 1) || p.want_h)) {
             double total = 0.0;
 #pragma unroll 2
             for (unsigned i = 0; i < V; i++) total += (double)zbuf[i];

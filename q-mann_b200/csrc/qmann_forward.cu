@@ -21,6 +21,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -71,6 +73,8 @@ struct qmann_model {
     signed char *dev_lut = nullptr;          // linear-map product tables (k_prep_lut), NULL when too large
     FwdParams base;                // everything but the per-call fields
     unsigned LPR, NW, smem_bytes;
+    unsigned NW_fast = 0;          // warps per CTA of k_forward_fast
+    unsigned tables_fast = 0;      // bytes of its shared-memory image
     unsigned rec_stride, off_rend, off_exc, off_ent, lcap;
     // chunk scratch
     unsigned chunk_cap;
@@ -148,11 +152,19 @@ int launch_forward(const qmann_model *m, const FwdParams &p, bool debug, cudaStr
     }
 }
 
+// The fast kernels may run more warps per SM than the general one when shared memory allows (NW_fast > 16: the 768-thread
+// instantiation, at most 85 registers per thread).
 template <int LPR, int MODE, bool SWAR>
 int launch_fast_t(const qmann_model *m, const FwdParams &p, cudaStream_t st)
 {
-    QCUDA(cudaFuncSetAttribute(k_forward_fast<LPR, MODE, SWAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_bytes));
-    k_forward_fast<LPR, MODE, SWAR><<<(unsigned)m->sm_count, m->NW * 32, m->smem_bytes, st>>>(p);
+    const unsigned smem = m->tables_fast + m->NW_fast * m->base.warp_bytes;
+    if (m->NW_fast > 16) {
+        QCUDA(cudaFuncSetAttribute(k_forward_fast<LPR, MODE, SWAR, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_forward_fast<LPR, MODE, SWAR, 768><<<(unsigned)m->sm_count, m->NW_fast * 32, smem, st>>>(p);
+    } else {
+        QCUDA(cudaFuncSetAttribute(k_forward_fast<LPR, MODE, SWAR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_forward_fast<LPR, MODE, SWAR, 512><<<(unsigned)m->sm_count, m->NW_fast * 32, smem, st>>>(p);
+    }
     count_launch();
     QCUDA(cudaPeekAtLastError());
     return QMANN_OK;
@@ -227,11 +239,17 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     p.offB = take((c.V + 1) * DP);                     // +1: the all-zero row idle gather lanes read
     for (unsigned h = 0; h < c.H; h++) { p.offA[h] = take((c.V + 1) * DP); p.offC[h] = take((c.V + 1) * DP); }
     for (unsigned h = 0; h < c.H; h++) p.offH[h] = c.lin_map ? take(c.d * HS) : 0;
-    p.offW = take(c.V * WS * 4);
     p.offCM[0] = take((c.V + 1) * 4);                  // cm10[V+1]: column maxima of A_h, three hops per word
     p.offTAU = take(128);
+    p.offW = take(c.V * WS * 4);
+    p.tables_bytes = off;                              // shared-memory image of the general kernel: everything up to here
+    unsigned W8S = round_up(c.d, 16);
+    if (((W8S / 16) & 1u) == 0) W8S += 16;             // odd number of 16-byte units: conflict-free lane-per-row reads
+    p.W8S = W8S;
+    p.w8_bytes = round_up(c.V * W8S, 16);
+    p.offW8 = take(p.w8_bytes);                        // global only; k_forward_fast places it at offW in its shared memory
     p.img_bytes = off;
-    p.tables_bytes = off;
+    const unsigned tables_fast = p.offW + p.w8_bytes;
     p.V = c.V; p.d = c.d; p.S_max = c.S_max; p.H = c.H; p.lin_map = c.lin_map; p.const_scale = c.const_scale;
     p.DP = DP; p.HS = HS; p.WS = WS;
     for (unsigned h = 0; h < c.H; h++) {
@@ -289,6 +307,18 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     p.warp_bytes = ent_region + fixed_warp;
     p.LW = LW; p.S_pad = S_pad;
     m->NW = NW;
+    // k_forward_fast keeps the int8 image of W instead of the fp32 rows in shared memory and needs 79 registers, so it can
+    // run up to 24 warps per SM where the general kernel runs NW (measured: +10 % at 24 over 16).  QMANN_FAST_WARPS caps it.
+    m->tables_fast = tables_fast;
+    m->NW_fast = NW;
+    {
+        unsigned cap = 24;
+        if (const char *e = getenv("QMANN_FAST_WARPS")) cap = (unsigned)std::max(1, atoi(e));
+        for (unsigned want : {24u, 20u, 16u, 12u, 8u, 6u, 4u, 2u, 1u}) {
+            if (want > cap) continue;
+            if ((size_t)tables_fast + (size_t)want * p.warp_bytes + 1024 <= (size_t)max_smem) { m->NW_fast = want; break; }
+        }
+    }
     m->smem_bytes = p.tables_bytes + NW * p.warp_bytes;
 
     // ---- quantise the weights ----
@@ -319,6 +349,29 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     }
     k_prep_ans<<<64, 256>>>(w->dev_W, reinterpret_cast<float *>(m->dev_img + p.offW), c.V, c.d, WS);
     count_launch();
+    {
+        // int8 image of W for the answer prefilter: W8 = rint(W / s), s = max|W| / 127 (host side, once)
+        std::vector<float> hw((size_t)c.V * c.d);
+        QCUDA(cudaMemcpy(hw.data(), w->dev_W, hw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        double wmax = 0.0;
+        bool finite = true;
+        for (float x : hw) { if (!std::isfinite(x)) finite = false; wmax = std::max(wmax, (double)std::fabs(x)); }
+        const char *env_pf = getenv("QMANN_ANS_PREFILTER");
+        p.w8_ok = (finite && wmax > 0.0 && !(env_pf && atoi(env_pf) == 0)) ? 1 : 0;
+        if (p.w8_ok) {
+            const double sc = wmax / 127.0;
+            std::vector<signed char> h8((size_t)p.w8_bytes, 0);
+            for (unsigned i = 0; i < c.V; i++)
+                for (unsigned j = 0; j < c.d; j++) h8[(size_t)i * W8S + j] = (signed char)std::lrint((double)hw[(size_t)i * c.d + j] / sc);
+            QCUDA(cudaMemcpy(m->dev_img + p.offW8, h8.data(), h8.size(), cudaMemcpyHostToDevice));
+            // 1e-5 (the window in which two logits can share the maximal probability) in units of the integer dot product;
+            // the final u has frac[H-1] fractional bits (frac_w[0] when there is no hop)
+            const unsigned fu_last = c.H ? c.frac[c.H - 1] : c.frac_w[0];
+            const double mu = 1e-5 * std::ldexp(1.0, (int)fu_last) / sc;
+            p.ans_margin = (mu < 1e9) ? (int)std::ceil(mu) + 1 : 0;
+            if (!(mu < 1e9)) p.w8_ok = 0;
+        }
+    }
     // count splitting (k_compact): per-column max |code| and the largest count every weight format represents
     QCUDA(cudaMalloc((void **)&m->dev_colmax, c.V));
     QCUDA(cudaMemset(m->dev_colmax, 0, c.V));
@@ -517,13 +570,18 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
                 // packed embedding + scorer first; stories with a row whose column maxima add up above 127 go to the unpacked kernel
                 FwdParams ps = p;
                 ps.img = m->dev_img_swar;
+                ps.tables_bytes = m->tables_fast;
                 ps.slow_list = m->dev_slow_list2; ps.slow_count = m->dev_counter + 3;
                 rc = launch_fast(m, ps, true, st);
                 if (rc) return rc;
                 p.work_list = m->dev_slow_list2; p.work_count = m->dev_counter + 3; p.counter = m->dev_counter + 4;
             }
             p.slow_list = m->dev_slow_list; p.slow_count = m->dev_slow_count;
-            rc = launch_fast(m, p, false, st);
+            {
+                FwdParams pf = p;
+                pf.tables_bytes = m->tables_fast;
+                rc = launch_fast(m, pf, false, st);
+            }
             if (rc) return rc;
             p.work_list = m->dev_slow_list; p.work_count = m->dev_slow_count; p.counter = m->dev_counter2;
         }

@@ -45,6 +45,10 @@ struct FwdParams {
     unsigned img_bytes;
     unsigned offB, offA[MAXH], offC[MAXH], offH[MAXH], offW;
     unsigned offCM[MAXH], offTAU;          // packed path of k_forward_fast: per-column max |code| of A_h, saturation thresholds
+    // answer-projection prefilter of k_forward_fast: int8 image of W (global offset offW8, rows of W8S bytes; it takes the
+    // place of the fp32 rows in that kernel's shared memory), ok flag, and 1e-5 in integer-dot units
+    unsigned offW8, W8S, w8_bytes;
+    int w8_ok, ans_margin;
     unsigned V, d, S_max, H, lin_map;
     int const_scale;
     unsigned DP, HS, WS;
@@ -811,7 +815,7 @@ __global__ void __launch_bounds__(512, 1) k_forward(const __grid_constant__ FwdP
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.img);
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (unsigned i = threadIdx.x; i < p.img_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        for (unsigned i = threadIdx.x; i < p.tables_bytes / 16; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
 
