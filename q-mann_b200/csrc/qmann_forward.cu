@@ -157,13 +157,16 @@ int launch_forward(const qmann_model *m, const FwdParams &p, bool debug, cudaStr
 template <int LPR, int MODE, bool SWAR>
 int launch_fast_t(const qmann_model *m, const FwdParams &p, cudaStream_t st)
 {
-    const unsigned smem = m->tables_fast + m->NW_fast * m->base.warp_bytes;
-    if (m->NW_fast > 16) {
+    // small launches do not need all the warps: about one story per warp and SM at least, 8 warps minimum
+    const unsigned per_sm = (p.n_stories + (unsigned)m->sm_count - 1) / (unsigned)m->sm_count;
+    const unsigned nw = std::min(m->NW_fast, std::max(std::min(8u, m->NW_fast), (per_sm + 3) / 4 * 4));
+    const unsigned smem = m->tables_fast + nw * m->base.warp_bytes;
+    if (nw > 16) {
         QCUDA(cudaFuncSetAttribute(k_forward_fast<LPR, MODE, SWAR, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_forward_fast<LPR, MODE, SWAR, 768><<<(unsigned)m->sm_count, m->NW_fast * 32, smem, st>>>(p);
+        k_forward_fast<LPR, MODE, SWAR, 768><<<(unsigned)m->sm_count, nw * 32, smem, st>>>(p);
     } else {
         QCUDA(cudaFuncSetAttribute(k_forward_fast<LPR, MODE, SWAR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_forward_fast<LPR, MODE, SWAR, 512><<<(unsigned)m->sm_count, m->NW_fast * 32, smem, st>>>(p);
+        k_forward_fast<LPR, MODE, SWAR, 512><<<(unsigned)m->sm_count, nw * 32, smem, st>>>(p);
     }
     count_launch();
     QCUDA(cudaPeekAtLastError());
