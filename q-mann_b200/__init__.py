@@ -4,3 +4,4 @@ The product is libqmann_b200.so (csrc/, C ABI in include/qmann_abi.h); this pack
 and mirrors the reference's layer interface for tests and benchmarks."""
 from . import synth  # noqa: F401
 from . import lib  # noqa: F401
+from . import babi  # noqa: F401

@@ -100,3 +100,38 @@ def test_ids_edge_cases(qmann, synth):
     # and the model keeps working afterwards
     pred, _, _ = model.infer_ids_host(ist.ids, ist.row_off, ist.ans, ist.n_sen)
     np.testing.assert_array_equal(pred, dense["pred"][:st.N].astype(np.uint32))
+
+
+def test_parsed_set_through_the_id_path(qmann, synth, tmp_path):
+    """A set in the reference's parsed-file grammar -> babi reader -> qmann_forward_ids, against the dense arenas built
+    literally as MemN2N/sample.c:544-572 does (test_babi_reader._literal_dense) through qmann_forward_batch."""
+    import torch
+    from test_babi_reader import _literal_dense, _write_set
+    babi = qmann.babi
+    rng = np.random.default_rng(9)
+    vocab = [f"w{i}" for i in range(24)]
+    samples = []
+    for _ in range(200):
+        ns = int(rng.integers(1, 21))
+        sens = [[vocab[int(k)] for k in rng.integers(0, len(vocab), size=int(rng.integers(1, 7)))] for _ in range(ns)]
+        samples.append((sens, [vocab[int(k)] for k in rng.integers(0, len(vocab), size=3)], [vocab[int(rng.integers(0, len(vocab)))]]))
+    path = str(tmp_path / "toy_test_set")
+    _write_set(path, samples)
+    data = babi.read_parsed_set(path, max_len=64)
+    d = babi.Dictionary(data)
+    dims = babi.dims_from_train(data, d)
+    ist = babi.to_id_stories(data, d, dims)
+    cfg = synth.ModelConfig(V=dims.dim_input, d=20, S_max=dims.max_line, V_dict=dims.dim_dict, mode=2)
+    w = synth.make_weights(cfg, 77, sigma=0.5)
+    m, q, a = _literal_dense(babi, data, d, dims)
+    st = synth.Stories(m=m, q=q, a=a, n_sen=ist.n_sen.copy(), ans=ist.ans.copy())
+    model = qmann.lib.Model(cfg, w)
+    dense = model.forward(model.upload(st), with_answers=True, want_h=True, debug=True)
+    ids = model.forward(model.upload_ids(ist), with_answers=True, want_h=True, debug=True)
+    torch.cuda.synchronize()
+    for k in KEYS:
+        np.testing.assert_array_equal(ids[k].cpu().numpy(), dense[k].cpu().numpy(), err_msg=k)
+    np.testing.assert_array_equal(ids["pred"].cpu().numpy()[:st.N], dense["pred"].cpu().numpy()[:st.N])
+    fast = model.forward(model.upload_ids(ist), with_answers=True, want_h=False, debug=False)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(fast["pred"].cpu().numpy()[:st.N], dense["pred"].cpu().numpy()[:st.N])
