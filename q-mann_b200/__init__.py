@@ -5,3 +5,4 @@ and mirrors the reference's layer interface for tests and benchmarks."""
 from . import synth  # noqa: F401
 from . import lib  # noqa: F401
 from . import babi  # noqa: F401
+from . import weights_io  # noqa: F401
