@@ -135,3 +135,15 @@ def test_parsed_set_through_the_id_path(qmann, synth, tmp_path):
     fast = model.forward(model.upload_ids(ist), with_answers=True, want_h=False, debug=False)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(fast["pred"].cpu().numpy()[:st.N], dense["pred"].cpu().numpy()[:st.N])
+
+
+def test_c_host_demo(qmann):
+    """examples/batched_demo.c: C host code (plain pointers, four cudart calls) through qmann_infer_host and
+    qmann_infer_ids_host on the same stories; built by __graft_entry__.build()."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "batched_demo")
+    if not os.path.exists(exe):
+        pytest.skip("examples/batched_demo has not been built (python -c 'import __graft_entry__ as g; g.build()')")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("DEMO_OK"), r.stdout + r.stderr
