@@ -23,8 +23,16 @@ d=256, 3 hops, slot-sharded across the ranks (strong scaling: the memory is fixe
 S/N slots), Q queries per step, two integer all-reduces per hop over NCCL.
 
 --impl reference: the reference has no runnable CPU forward, so this arm times
-the CPU restatement of its CUDA arithmetic (oracle/, kind "port") on all host threads, on a bounded
-sample of the same workload.
+the CPU restatement of its CUDA arithmetic (oracle/, kind "port") on all host threads (the thread count is passed
+explicitly: torchrun exports OMP_NUM_THREADS=1), on a bounded sample of the same workload.
+--impl reference_gpu: the reference's OWN CUDA path (lib/layer.c + lib/layer_cuda.cu compiled unmodified for
+sm_100a into oracle/_ref/ref_harness_refcuda, 31 launches per story) timed on this box's GPU on a bounded sample.
+
+The default (C1-C4) line also carries: `roofline` for the WHOLE step (algorithmic bytes of the step / step time) with the
+kernels broken out, `path_share` (which kernel tier finished how many stories), `sensitivity` (the same step with
+N(0,1) and N(0,2) weights, whose codes saturate more and leave the packed tier), `e2e_ids` (host word-id lists in,
+predictions out), `reference_gpu` (N=1) and `c5`: the slot-sharded large-memory workload (the one with a collective)
+measured in the same process group at Q = 64 and 1024, sharded == unsharded checked before timing.
 """
 from __future__ import annotations
 
@@ -147,16 +155,49 @@ def dist_setup(n_gpus: int):
     return rank, world, local
 
 
+def host_threads():
+    """Host threads this process may use.  Passed explicitly to the oracle: torch.distributed.run exports
+    OMP_NUM_THREADS=1, which would silently make the CPU arm single-threaded (round-1 SCALE bug)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_rate(synth, cfg, w, S, sample, threads=0):
     """stories/s of the CPU restatement (oracle/) on `sample` stories of the workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import qmo
     st = synth.make_stories(cfg, sample, 0x5EED1000 + 99, S=S)
     qmo.lib()
+    if threads <= 0:
+        threads = host_threads()
     t0 = time.perf_counter()
     out = qmo.forward(cfg, w, st, dump=False, n_threads=threads)
     dt = time.perf_counter() - t0
-    return sample / dt, dt, qmo.lib().qmo_max_threads() if threads <= 0 else threads, out
+    return sample / dt, dt, threads, out
+
+
+def reference_gpu_rate(synth, cfg, w, S, sample=2000, reps=2):
+    """stories/s of the reference's own CUDA path (oracle/_ref/ref_harness_refcuda: the unmodified lib/layer.c +
+    lib/layer_cuda.cu, one story per 31 launches) on `sample` stories of the workload.  None when it was not built."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_harness_refcuda")
+    if not os.path.exists(exe):
+        return None
+    st = synth.make_stories(cfg, sample, 0x5EED1000 + 98, S=S)
+    with tempfile.TemporaryDirectory() as td:
+        case, dump = os.path.join(td, "c.bin"), os.path.join(td, "d.bin")
+        synth.write_case(case, cfg, w, st)
+        try:
+            r = subprocess.run([exe, case, dump, str(reps)], check=True, capture_output=True, timeout=600, text=True)
+        except Exception as e:          # noqa: BLE001
+            return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    for line in r.stdout.splitlines():
+        if line.startswith("TIME_S"):
+            sec = float(line.split()[1])
+            return {"value": sample / sec, "unit": UNIT, "sample": f"{sample} stories, {reps} timed passes after one dumping pass",
+                    "s_per_pass": sec, "kind": "reference CUDA path rebuilt for sm_100a (oracle/Makefile), unmodified"}
+    return {"unavailable": "no TIME_S line"}
 
 
 # ---------------------------------------------------------------------------------------------------

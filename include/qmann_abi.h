@@ -179,6 +179,17 @@ typedef struct {
     float *dev_u;      /* [H][N][d]         */
     float *dev_z;      /* [N][V]            */
     float *dev_h;      /* [N][V]            */
+    /* -- what the PRODUCTION kernels computed (round 2) -- */
+    uint8_t *dev_pcode;  /* [H][sum_sen]  code of Q_f(p) per slot; the slots with a non-zero code are the selected slots of
+                                          the weighted read (lib/layer_cuda.cu:561)                                     */
+    uint8_t *dev_path;   /* [N]           kernel tier that produced the prediction: 1 packed, 2 unpacked, 3 general    */
+    uint8_t *dev_cand;   /* [N][V]        answer rows whose fp32 logit was computed: 1 = prefilter candidate, 2 = every
+                                          row was computed (near-tie, h[y] requested, general kernel), 0 = row skipped  */
+    uint32_t production; /* 0: every story through the instrumented general kernel (all members above are filled);
+                            1: the production tiers (k_story packed / unpacked, then the general kernel for what they
+                               decline) with dumps switched on: dev_u0, dev_s, dev_pcode, dev_o, dev_g, dev_u, dev_z (exact
+                               rows; -inf where skipped), dev_cand, dev_path.  dev_M/dev_C/dev_p/dev_h are written only for
+                               the stories the general kernel finished (dev_path == 3).                                 */
 } qmann_debug;
 
 typedef struct qmann_model qmann_model;   /* quantised weight images resident in HBM */
@@ -224,6 +235,23 @@ int  qmann_infer_ids_host(qmann_model *m, const uint16_t *ids_host, const uint32
  * (batch sharding across GPUs: stories are independent, no collective). */
 int  qmann_shard_plan(const uint32_t *n_sen, uint32_t N, uint32_t world, uint32_t rank,
                       uint32_t *first, uint32_t *count);
+
+/* Device-side error flag of the model.  The asynchronous entries (qmann_forward_batch, qmann_forward_ids) cannot
+ * return what a kernel finds: a story that overflows the compaction heap or names an id >= V gets the prediction
+ * 0xFFFFFFFF (QMANN_PRED_NONE) in dev_pred and sets the flag.  qmann_check_errors() synchronises `stream`, stores the
+ * flag in *flags (0 = clean), clears it and returns QMANN_OK, or QMANN_E_CUDA if the stream itself failed.  The host
+ * entries (qmann_infer_host, qmann_infer_ids_host) do this themselves: they return a QMANN_E_* code for the call in
+ * which it happened and the next call starts clean.
+ *
+ * Threading: a qmann_model owns ONE set of scratch buffers (compact records, heap, work lists, staging arenas), so it
+ * supports one forward in flight at a time.  Calls on the same model must be issued from one thread and on one stream
+ * (or be externally ordered); use one model per stream for concurrency (the weight images are a few hundred KB). */
+#define QMANN_PRED_NONE 0xFFFFFFFFu
+int  qmann_check_errors(qmann_model *m, void *stream, uint32_t *flags);
+
+/* Stories that entered each tier of the production path since the last call (then reset): tiers[0] packed kernel,
+ * tiers[1] unpacked kernel, tiers[2] general kernel.  Synchronises `stream`. */
+int  qmann_path_counts(qmann_model *m, void *stream, uint64_t tiers[3]);
 
 /* Optional per-kernel timing: while enabled, qmann_forward_batch/qmann_infer_host bracket each of
  * their two kernels with CUDA events on the launching stream.  qmann_profile_read() synchronises

@@ -1,17 +1,15 @@
 // qmann_forward.cu -- batched quantized MemN2N inference forward for sm_100a (include/qmann_abi.h
 // part 2).  Replaces the reference's one-story-at-a-time host loop (MemN2N/MemN2N.c:2377-2703,
-// 31 kernel launches per story) by two kernels per chunk of stories:
+// 31 kernel launches per story) by tiers of kernels per chunk of stories:
 //
-//   k_compact  : streams the dense fp32 bag-of-words arenas (the reference's boundary format,
-//                MemN2N.c:2294-2350) once, HBM-bound, and writes per story an ordered list of its
-//                non-zero (column, value) entries with per-row end offsets.
-//   k_forward  : one warp per story, persistent CTAs, all quantised weight tables resident in
-//                shared memory as int8 codes.  Per hop: bag-of-words embedding as a gather-and-sum
-//                of int8 table rows (128-bit shared loads, dp4a accumulation), scorer (fixed-point
-//                dot product or Hamming/approximate similarity), fp32 softmax with the reference's
-//                sequential double-precision denominator, quantised weights, weighted read over the
-//                slots whose quantised weight is non-zero, linear mapping, saturating update; then
-//                the fp32 answer projection in the reference's summation order and the argmax.
+//   k_story    : (qmann_fast.cuh) the production kernel: one warp per story streams the story's dense fp32
+//                bag-of-words rows (the reference's boundary format, MemN2N.c:2294-2350) from HBM with bulk
+//                asynchronous copies, compacts them in shared memory and runs the whole forward; packed
+//                (SWAR) tier first, unpacked tier for what that declines.
+//   k_compact  : dense arenas -> compact records in global memory, for the stories k_story declines
+//                (fractional values, large counts, very dense stories) and for the instrumented pass.
+//   k_forward  : the general kernel (every input, optional dumps of every intermediate): one warp per story,
+//                persistent CTAs, all quantised weight tables resident in shared memory as int8 codes.
 //
 // Arithmetic follows SURVEY.md Appendix A (integer forms proven against the reference by
 // tests/golden/kat_*.npz); every formula cites the reference line it reproduces.
@@ -69,28 +67,32 @@ struct qmann_model {
     qmann_config cfg;
     int device;
     int sm_count;
-    unsigned char *dev_img;
+    int max_smem = 0;
+    unsigned char *dev_img = nullptr;
     signed char *dev_lut = nullptr;          // linear-map product tables (k_prep_lut), NULL when too large
     FwdParams base;                // everything but the per-call fields
     unsigned LPR, NW, smem_bytes;
-    unsigned NW_fast = 0;          // warps per CTA of k_forward_fast
-    unsigned tables_fast = 0;      // bytes of its shared-memory image
+    unsigned NW_fast = 0;          // warps per CTA of k_story
+    unsigned long long *dev_path_count = nullptr;   // [4] stories that entered each tier (qmann_path_counts)
+    unsigned story_chunk_cap = 0;  // stories per launch of the dense production path (records are needed only for declined stories)
+    double prof_acc_c = 0.0, prof_acc_f = 0.0;      // folded event pairs
+    size_t prof_pairs = 0;
     unsigned rec_stride, off_rend, off_exc, off_ent, lcap;
     // chunk scratch
     unsigned chunk_cap;
-    unsigned char *dev_rec;
-    uint2 *dev_heap;
+    unsigned char *dev_rec = nullptr;
+    uint2 *dev_heap = nullptr;
     unsigned long long heap_cap;
     // control block (one 32-byte memset per chunk): heap_used u64 | counter | slow_count | counter2
-    unsigned long long *dev_heap_used;
-    unsigned *dev_counter, *dev_slow_count, *dev_counter2, *dev_err;
+    unsigned long long *dev_heap_used = nullptr;
+    unsigned *dev_counter = nullptr, *dev_err = nullptr;
     unsigned *dev_slow_list = nullptr;       // [chunk_cap] chunk indices the fast kernel left to the general one
     unsigned *dev_slow_list2 = nullptr;      // [chunk_cap] chunk indices the packed kernel left to the unpacked fast kernel
     unsigned char *dev_img_swar = nullptr;   // image with biased A_h tables (packed path of k_forward_fast)
     bool swar_ok = false;
     bool fast_ok = false;                    // every weight format has an integer bit (Q_w(1.0) = 2^frac_w)
     unsigned char *dev_colmax = nullptr;     // [V] max |code| per column over all embedding tables (count splitting)
-    unsigned nmax = 0;
+    unsigned nmax = 0, split_lim = 127;
     // qmann_infer_host staging (grow-only device arenas, two streams)
     float *e2e_m = nullptr, *e2e_q = nullptr, *e2e_a = nullptr, *e2e_h = nullptr;
     uint32_t *e2e_pred = nullptr, *e2e_match = nullptr;
@@ -121,6 +123,10 @@ struct qmann_batch {
 
 namespace {
 unsigned round_up(unsigned v, unsigned m) { return (v + m - 1) / m * m; }
+constexpr unsigned CTRL_BYTES = 128;          // control block of a chunk: heap_used u64 | 30 x u32 counters
+// counter slots: 0 packed tier claims, 1 unpacked tier claims, 2 packed->unpacked list length, 3 ->general list length,
+// 8.. general-kernel claims per slice of the declined list
+constexpr unsigned CT_PACKED = 0, CT_UNPACKED = 1, CT_LIST2 = 2, CT_LIST1 = 3, CT_GENERAL0 = 8;
 
 template <int LPR, int MODE>
 int launch_forward_t(const qmann_model *m, const FwdParams &p, bool debug, cudaStream_t st)
@@ -152,40 +158,53 @@ int launch_forward(const qmann_model *m, const FwdParams &p, bool debug, cudaStr
     }
 }
 
-// The fast kernels may run more warps per SM than the general one when shared memory allows (NW_fast > 16: the 768-thread
-// instantiation, at most 85 registers per thread).
-template <int LPR, int MODE, bool SWAR>
-int launch_fast_t(const qmann_model *m, const FwdParams &p, cudaStream_t st)
+// k_story: up to 24 warps per SM where shared memory and the 80-register budget allow (MAXT 768), 16 otherwise; the DUMP
+// instantiations exist for MAXT 512 only.
+template <int LPR, int MODE, bool SWAR, bool DENSE>
+int launch_story_t(const qmann_model *m, const FwdParams &p, bool dump, cudaStream_t st)
 {
     // small launches do not need all the warps: about one story per warp and SM at least, 8 warps minimum
     const unsigned per_sm = (p.n_stories + (unsigned)m->sm_count - 1) / (unsigned)m->sm_count;
-    const unsigned nw = std::min(m->NW_fast, std::max(std::min(8u, m->NW_fast), (per_sm + 3) / 4 * 4));
-    const unsigned smem = m->tables_fast + nw * m->base.warp_bytes;
-    if (nw > 16) {
-        QCUDA(cudaFuncSetAttribute(k_forward_fast<LPR, MODE, SWAR, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_forward_fast<LPR, MODE, SWAR, 768><<<(unsigned)m->sm_count, nw * 32, smem, st>>>(p);
-    } else {
-        QCUDA(cudaFuncSetAttribute(k_forward_fast<LPR, MODE, SWAR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_forward_fast<LPR, MODE, SWAR, 512><<<(unsigned)m->sm_count, nw * 32, smem, st>>>(p);
-    }
+    unsigned nw = std::min(m->NW_fast, std::max(std::min(8u, m->NW_fast), (per_sm + 3) / 4 * 4));
+    if (dump) nw = std::min(nw, 16u);
+    const unsigned smem = p.fl.tables_bytes + nw * p.fl.warp_bytes;
+    const unsigned grid = (unsigned)m->sm_count;
+#define QM_LAUNCH(DUMP_, MAXT_)                                                                                              \
+    do {                                                                                                                      \
+        static bool attr_done = false;                                                                                        \
+        if (!attr_done) {                                                                                                     \
+            QCUDA(cudaFuncSetAttribute(k_story<LPR, MODE, SWAR, DENSE, DUMP_, MAXT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->max_smem)); \
+            attr_done = true;                                                                                                 \
+        }                                                                                                                     \
+        k_story<LPR, MODE, SWAR, DENSE, DUMP_, MAXT_><<<grid, nw * 32, smem, st>>>(p);                                        \
+    } while (0)
+    if (dump) QM_LAUNCH(true, 512);
+    else if (nw > 16) QM_LAUNCH(false, 768);
+    else QM_LAUNCH(false, 512);
+#undef QM_LAUNCH
     count_launch();
     QCUDA(cudaPeekAtLastError());
     return QMANN_OK;
 }
-template <int LPR>
-int launch_fast_l(const qmann_model *m, const FwdParams &p, bool swar, cudaStream_t st)
+template <int LPR, bool DENSE>
+int launch_story_l(const qmann_model *m, const FwdParams &p, bool swar, bool dump, cudaStream_t st)
 {
-    if (swar) return launch_fast_t<LPR, 2, true>(m, p, st);
-    return m->cfg.mode == 3 ? launch_fast_t<LPR, 3, false>(m, p, st) : launch_fast_t<LPR, 2, false>(m, p, st);
+    if (swar) return launch_story_t<LPR, 2, true, DENSE>(m, p, dump, st);
+    return m->cfg.mode == 3 ? launch_story_t<LPR, 3, false, DENSE>(m, p, dump, st) : launch_story_t<LPR, 2, false, DENSE>(m, p, dump, st);
 }
-int launch_fast(const qmann_model *m, const FwdParams &p, bool swar, cudaStream_t st)
+template <bool DENSE>
+int launch_story_d(const qmann_model *m, const FwdParams &p, bool swar, bool dump, cudaStream_t st)
 {
     switch (m->LPR) {
-        case 4: return launch_fast_l<4>(m, p, swar, st);
-        case 8: return launch_fast_l<8>(m, p, swar, st);
-        case 16: return launch_fast_l<16>(m, p, swar, st);
-        default: return launch_fast_l<32>(m, p, swar, st);
+        case 4: return launch_story_l<4, DENSE>(m, p, swar, dump, st);
+        case 8: return launch_story_l<8, DENSE>(m, p, swar, dump, st);
+        case 16: return launch_story_l<16, DENSE>(m, p, swar, dump, st);
+        default: return launch_story_l<32, DENSE>(m, p, swar, dump, st);
     }
+}
+int launch_story(const qmann_model *m, const FwdParams &p, bool swar, bool dense, bool dump, cudaStream_t st)
+{
+    return dense ? launch_story_d<true>(m, p, swar, dump, st) : launch_story_d<false>(m, p, swar, dump, st);
 }
 }  // namespace
 
@@ -195,10 +214,21 @@ const char *qmann_last_error(void) { return g_err.c_str(); }
 const char *qmann_version(void) { return "qmann_b200 0.1 (sm_100a)"; }
 uint64_t qmann_launch_count(void) { return g_launches.load(); }
 
+static int model_build(qmann_model *m, const qmann_config *cfg, const qmann_weights *w);
+
 int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_weights *w)
 {
     if (!out || !cfg || !w) return fail(QMANN_E_ARG, "null argument");
     *out = nullptr;
+    qmann_model *m = new qmann_model();
+    const int rc = model_build(m, cfg, w);
+    if (rc != QMANN_OK) { qmann_model_destroy(m); return rc; }      // frees whatever the failed build had allocated
+    *out = m;
+    return QMANN_OK;
+}
+
+static int model_build(qmann_model *m, const qmann_config *cfg, const qmann_weights *w)
+{
     const qmann_config &c = *cfg;
     if (c.H == 0 || c.H > MAXH) return fail(QMANN_E_ARG, "H must be in 1..8");
     if (c.mode != 2 && c.mode != 3) return fail(QMANN_E_ARG, "attention mode must be 2 (fixed-point dot) or 3 (Hamming/approximate)");
@@ -219,7 +249,6 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     for (unsigned h = 0; h < c.H; h++)
         if (!w->dev_A[h] || !w->dev_C[h] || (c.lin_map && !w->dev_Hm[h])) return fail(QMANN_E_ARG, "missing per-hop weight pointer");
 
-    qmann_model *m = new qmann_model();
     m->cfg = c;
     QCUDA(cudaGetDevice(&m->device));
     cudaDeviceProp prop;
@@ -252,7 +281,6 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     p.w8_bytes = round_up(c.V * W8S, 16);
     p.offW8 = take(p.w8_bytes);                        // global only; k_forward_fast places it at offW in its shared memory
     p.img_bytes = off;
-    const unsigned tables_fast = p.offW + p.w8_bytes;
     p.V = c.V; p.d = c.d; p.S_max = c.S_max; p.H = c.H; p.lin_map = c.lin_map; p.const_scale = c.const_scale;
     p.DP = DP; p.HS = HS; p.WS = WS;
     for (unsigned h = 0; h < c.H; h++) {
@@ -270,6 +298,7 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     p.o_rend = 0;  // placeholder, set below
     int max_smem = 0;
     QCUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+    m->max_smem = max_smem;
     unsigned NW = 0, LW = 0;
     unsigned fixed_warp = 0;
     {
@@ -299,7 +328,6 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
         break;
     }
     if (NW == 0) {
-        delete m;
         return fail(QMANN_E_NOMEM, "model tables (" + std::to_string(p.tables_bytes) + " B) plus per-warp scratch do not fit the SM's " +
                                        std::to_string(max_smem) + " B of shared memory");
     }
@@ -310,18 +338,7 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     p.warp_bytes = ent_region + fixed_warp;
     p.LW = LW; p.S_pad = S_pad;
     m->NW = NW;
-    // k_forward_fast keeps the int8 image of W instead of the fp32 rows in shared memory and needs 79 registers, so it can
-    // run up to 24 warps per SM where the general kernel runs NW (measured: +10 % at 24 over 16).  QMANN_FAST_WARPS caps it.
-    m->tables_fast = tables_fast;
-    m->NW_fast = NW;
-    {
-        unsigned cap = 24;
-        if (const char *e = getenv("QMANN_FAST_WARPS")) cap = (unsigned)std::max(1, atoi(e));
-        for (unsigned want : {24u, 20u, 16u, 12u, 8u, 6u, 4u, 2u, 1u}) {
-            if (want > cap) continue;
-            if ((size_t)tables_fast + (size_t)want * p.warp_bytes + 1024 <= (size_t)max_smem) { m->NW_fast = want; break; }
-        }
-    }
+    m->NW_fast = 0;            // sized below, once count splitting and the packed path are known
     m->smem_bytes = p.tables_bytes + NW * p.warp_bytes;
 
     // ---- quantise the weights ----
@@ -393,6 +410,11 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
         }
         m->nmax = unit_ok ? nmax : 0;
         m->fast_ok = unit_ok;
+        // n unit entries stand for a count n only while n * max|code| stays inside EVERY hop's weight format
+        // (the reference clamps each product Q_w(Q_w(n) * Q_w(T)) to that hop's limit, lib/layer_cuda.cu:120)
+        unsigned sl = 127;
+        for (unsigned h = 0; h < c.H; h++) sl = std::min(sl, (unsigned)p.lw[h]);
+        m->split_lim = sl;
     }
     // packed path (mode 2): every hop with an 8-bit memory/addressing format, two fractional bits in the query operand and
     // |frac_att - frac_w| <= 1.  QMANN_SWAR=0 keeps the unpacked kernel only (A/B tests).
@@ -416,6 +438,55 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
             m->swar_ok = true;
         }
     }
+    // ---- production kernel k_story: shared-memory image (A_h, column maxima, tau, int8 W) and per-warp scratch ----
+    {
+        FastLayout &fl = p.fl;
+        unsigned t = 0;
+        auto ttake = [&](unsigned bytes) { unsigned o_ = t; t += round_up(bytes, 16); return o_; };
+        for (unsigned h = 0; h < c.H; h++) fl.sA[h] = ttake((c.V + 1) * DP);
+        fl.sCM = ttake((c.V + 1) * 4);
+        fl.sTAU = ttake(128);
+        fl.sW8 = ttake(p.w8_bytes);
+        fl.tables_bytes = round_up(t, 128);
+        const unsigned row_bytes = c.V * 4;
+        unsigned R = std::max(1u, 2048u / row_bytes), NB = 2;
+        if (const char *e = getenv("QMANN_STAGE_ROWS")) R = (unsigned)std::max(1, atoi(e));
+        if (const char *e = getenv("QMANN_STAGE_BUFS")) NB = (unsigned)std::min(8, std::max(1, atoi(e)));
+        fl.R = R; fl.NB = NB;
+        fl.buf_bytes = round_up(R * row_bytes + 32, 128);
+        unsigned o2 = 0;
+        auto w2 = [&](unsigned bytes, unsigned al = 16) { o2 = round_up(o2, al); unsigned r_ = o2; o2 += bytes; return r_; };
+        // entry list first (16-bit table-row offsets); the region doubles as zbuf[V] in the answer phase
+        const unsigned want_ent = std::min(65535u, round_up(8 * (c.S_max + 1), 32));
+        const unsigned ent_bytes = round_up(std::max(want_ent * 2, c.V * 4), 16);
+        w2(ent_bytes);
+        fl.LW = ent_bytes / 2;
+        fl.o_rend = w2((c.S_max + 2) * 2);
+        fl.o_sc = w2(S_pad * 4); fl.o_ex = w2(S_pad * 4); fl.o_pq = w2(S_pad);
+        fl.o_uvec = w2(DP); fl.o_ub32 = w2(DP * 4); fl.o_ovec = w2(DP); fl.o_ufl = w2(DP * 4);
+        fl.o_zent = w2(16);
+        fl.o_brow = w2(c.H * S_pad); fl.o_perm = w2(S_pad * 2); fl.o_cnt = w2(20 * 4);
+        fl.o_bar = w2(8 * NB, 8);
+        fl.o_stage = w2(NB * fl.buf_bytes, 128);
+        fl.warp_bytes = round_up(o2, 128);
+        // entries are 16-bit offsets column * DP
+        if ((size_t)(c.V + 1) * DP > 65535u) m->fast_ok = false;
+        unsigned cap = 24;
+        if (const char *e = getenv("QMANN_FAST_WARPS")) cap = (unsigned)std::max(1, atoi(e));
+        m->NW_fast = 0;
+        for (unsigned want : {24u, 22u, 20u, 18u, 16u, 14u, 12u, 10u, 8u, 6u, 4u, 2u, 1u}) {
+            if (want > cap) continue;
+            if ((size_t)fl.tables_bytes + (size_t)want * fl.warp_bytes + 1024 <= (size_t)max_smem) { m->NW_fast = want; break; }
+        }
+        if (m->NW_fast == 0) m->fast_ok = false;
+        p.colmax = m->dev_colmax; p.nmax = m->nmax; p.split_lim = m->split_lim;
+        const char *efs = getenv("QMANN_FAST_SOFTMAX");
+        p.fast_softmax = (efs && atoi(efs) == 0) ? 0 : 1;
+        p.pf_dist = 384; p.pf_mode = 1;
+        if (const char *e = getenv("QMANN_PF_DIST")) p.pf_dist = (unsigned)std::max(0, atoi(e));
+        if (const char *e = getenv("QMANN_PF_MODE")) p.pf_mode = (unsigned)std::max(0, atoi(e));
+        if (p.pf_dist == 0) p.pf_mode = 0;
+    }
     QCUDA(cudaPeekAtLastError());
     QCUDA(cudaDeviceSynchronize());
     p.img = m->dev_img;
@@ -426,21 +497,22 @@ int qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_w
     m->off_exc = round_up(REC_HDR_BYTES + (c.S_max + 2) * 2, 16);
     m->off_ent = m->off_exc + MAX_EXC * 8;
     m->rec_stride = round_up(m->off_ent + m->lcap * 4, 16);
-    m->chunk_cap = 32768;
+    m->chunk_cap = 32768;                    // records held at a time (ids input, instrumented pass, declined stories)
+    m->story_chunk_cap = 8 * m->chunk_cap;   // stories per launch of the dense production path
     QCUDA(cudaMalloc((void **)&m->dev_rec, (size_t)m->chunk_cap * m->rec_stride));
     m->heap_cap = 8ull << 20;                                        // 8 Mi entries = 64 MiB
     QCUDA(cudaMalloc((void **)&m->dev_heap, m->heap_cap * sizeof(uint2)));
-    QCUDA(cudaMalloc((void **)&m->dev_heap_used, 32));
+    // control block (one memset per chunk): heap_used u64 | 30 x u32 counters
+    QCUDA(cudaMalloc((void **)&m->dev_heap_used, CTRL_BYTES));
     m->dev_counter = reinterpret_cast<unsigned *>(m->dev_heap_used + 1);
-    m->dev_slow_count = m->dev_counter + 1;
-    m->dev_counter2 = m->dev_counter + 2;
-    QCUDA(cudaMalloc((void **)&m->dev_slow_list, (size_t)m->chunk_cap * sizeof(unsigned)));
-    QCUDA(cudaMalloc((void **)&m->dev_slow_list2, (size_t)m->chunk_cap * sizeof(unsigned)));
+    QCUDA(cudaMalloc((void **)&m->dev_slow_list, (size_t)m->story_chunk_cap * sizeof(unsigned)));
+    QCUDA(cudaMalloc((void **)&m->dev_slow_list2, (size_t)m->story_chunk_cap * sizeof(unsigned)));
     QCUDA(cudaMalloc((void **)&m->dev_err, sizeof(unsigned)));
     QCUDA(cudaMemset(m->dev_err, 0, sizeof(unsigned)));
+    QCUDA(cudaMalloc((void **)&m->dev_path_count, 4 * sizeof(unsigned long long)));
+    QCUDA(cudaMemset(m->dev_path_count, 0, 4 * sizeof(unsigned long long)));
     p.rec = m->dev_rec; p.rec_stride = m->rec_stride; p.off_rend = m->off_rend; p.off_exc = m->off_exc; p.off_ent = m->off_ent;
-    p.heap = m->dev_heap; p.counter = m->dev_counter; p.err_flag = m->dev_err;
-    *out = m;
+    p.heap = m->dev_heap; p.counter = m->dev_counter; p.err_flag = m->dev_err; p.path_count = m->dev_path_count;
     return QMANN_OK;
 }
 
@@ -448,7 +520,7 @@ void qmann_model_destroy(qmann_model *m)
 {
     if (!m) return;
     cudaFree(m->dev_img); cudaFree(m->dev_lut); cudaFree(m->dev_rec); cudaFree(m->dev_heap); cudaFree(m->dev_heap_used);
-    cudaFree(m->dev_slow_list); cudaFree(m->dev_slow_list2); cudaFree(m->dev_img_swar); cudaFree(m->dev_err); cudaFree(m->dev_colmax);
+    cudaFree(m->dev_path_count); cudaFree(m->dev_slow_list); cudaFree(m->dev_slow_list2); cudaFree(m->dev_img_swar); cudaFree(m->dev_err); cudaFree(m->dev_colmax);
     if (m->host_batch) qmann_batch_destroy(m->host_batch);
     cudaFree(m->ids_dev); cudaFree(m->rowoff_dev); cudaFree(m->ans_dev); cudaFree(m->e2e_pred2); cudaFree(m->e2e_h2);
     cudaFree(m->e2e_m); cudaFree(m->e2e_q); cudaFree(m->e2e_a); cudaFree(m->e2e_h); cudaFree(m->e2e_pred); cudaFree(m->e2e_match);
@@ -520,25 +592,47 @@ struct FwdInput {
     const uint32_t *dev_row_off = nullptr, *dev_ans = nullptr;
 };
 
+// Event triples of the optional profile are folded into running sums before the vector can grow without bound.
+static int profile_fold(qmann_model *m)
+{
+    for (size_t i = 0; i + 3 <= m->prof_used; i += 3) {
+        float a = 0.f, b2 = 0.f;
+        QCUDA(cudaEventSynchronize(m->prof_events[i + 2]));
+        QCUDA(cudaEventElapsedTime(&a, m->prof_events[i], m->prof_events[i + 1]));
+        QCUDA(cudaEventElapsedTime(&b2, m->prof_events[i + 1], m->prof_events[i + 2]));
+        m->prof_acc_c += a; m->prof_acc_f += b2;
+    }
+    m->prof_pairs += m->prof_used / 3;
+    m->prof_used = 0;
+    return QMANN_OK;
+}
+
 // Forward of stories [first, first+count) of the batch; data pointers are the FULL arenas.
+//
+// Production path (dbg == NULL or dbg->production):
+//   dense input, 16-byte aligned arenas:  k_story<packed, DENSE> -> k_story<unpacked, DENSE> on what it declines ->
+//                                         k_compact + k_forward (general) on what that declines, in slices of chunk_cap records
+//   word-id input / unaligned arenas:     k_ids_compact | k_compact over the chunk, then k_story<.., RECORD> tiers, k_forward
+// Instrumented path (dbg given, production == 0): k_compact | k_ids_compact, then k_forward<DEBUG> for every story.
 static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, uint32_t count, const FwdInput &in,
                          uint32_t *dev_pred, float *dev_h_true, uint32_t *dev_match, const qmann_debug *dbg, cudaStream_t st)
 {
-    const bool debug = dbg != nullptr;
+    const bool production = (dbg == nullptr) || dbg->production != 0;
+    const bool dump = dbg != nullptr;
     const float *dev_m = in.dev_m, *dev_q = in.dev_q, *dev_a = in.dev_a;
     const bool vec4 = (m->cfg.V % 4 == 0) && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 16 == 0);
     const bool vec2 = (m->cfg.V % 2 == 0) && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 8 == 0);
-    for (uint32_t s0 = first; s0 < first + count; s0 += m->chunk_cap) {
-        const uint32_t n = std::min<uint32_t>(m->chunk_cap, first + count - s0);
-        CompactParams cp;
-        cp.m = dev_m; cp.q = dev_q; cp.a = dev_a; cp.sen_off = b->dev_sen_off; cp.V = m->cfg.V; cp.S_max = m->cfg.S_max;
-        cp.story0 = s0; cp.n_stories = n; cp.rec = m->dev_rec; cp.rec_stride = m->rec_stride; cp.off_rend = m->off_rend;
-        cp.off_exc = m->off_exc; cp.off_ent = m->off_ent; cp.lcap = m->lcap; cp.heap = m->dev_heap; cp.heap_cap = m->heap_cap;
-        cp.heap_used = m->dev_heap_used; cp.colmax = m->dev_colmax; cp.nmax = m->nmax;
-        QCUDA(cudaMemsetAsync(m->dev_heap_used, 0, 32, st));
-        const unsigned cblocks = std::min<unsigned>((n + 7) / 8, (unsigned)m->sm_count * 8);
+    const bool fast = production && m->fast_ok && m->NW_fast > 0;
+    const char *env_stream = getenv("QMANN_DENSE_STREAM");
+    const bool stream_dense = fast && !in.dev_ids && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 16 == 0) && !(env_stream && atoi(env_stream) == 0);
+    const uint32_t cap = stream_dense ? m->story_chunk_cap : m->chunk_cap;
+    unsigned *ctr = m->dev_counter;
+    for (uint32_t s0 = first; s0 < first + count; s0 += cap) {
+        const uint32_t n = std::min<uint32_t>(cap, first + count - s0);
+        QCUDA(cudaMemsetAsync(m->dev_heap_used, 0, CTRL_BYTES, st));
         cudaEvent_t *pe = nullptr;
         if (m->profile) {
+            if (m->prof_used + 3 > 3 * 1024) { const int rcf = profile_fold(m); if (rcf) return rcf; }
             if (m->prof_used + 3 > m->prof_events.size()) {
                 for (int k = 0; k < 3; k++) { cudaEvent_t e; QCUDA(cudaEventCreate(&e)); m->prof_events.push_back(e); }
             }
@@ -546,50 +640,88 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
             m->prof_used += 3;
             QCUDA(cudaEventRecord(pe[0], st));
         }
-        if (in.dev_ids) {
-            IdsParams ip;
-            ip.ids = in.dev_ids; ip.row_off = in.dev_row_off; ip.ans = in.dev_ans; ip.sen_off = b->dev_sen_off; ip.V = m->cfg.V;
-            ip.story0 = s0; ip.n_stories = n; ip.rec = m->dev_rec; ip.rec_stride = m->rec_stride; ip.off_rend = m->off_rend;
-            ip.off_exc = m->off_exc; ip.off_ent = m->off_ent; ip.lcap = m->lcap; ip.heap = m->dev_heap; ip.heap_cap = m->heap_cap;
-            ip.heap_used = m->dev_heap_used; ip.colmax = m->dev_colmax; ip.nmax = m->nmax;
-            k_ids_compact<<<cblocks, 256, 0, st>>>(ip);
+        auto compact_params = [&]() {
+            CompactParams cp;
+            cp.m = dev_m; cp.q = dev_q; cp.a = dev_a; cp.sen_off = b->dev_sen_off; cp.V = m->cfg.V; cp.S_max = m->cfg.S_max;
+            cp.story0 = s0; cp.n_stories = n; cp.rec = m->dev_rec; cp.rec_stride = m->rec_stride; cp.off_rend = m->off_rend;
+            cp.off_exc = m->off_exc; cp.off_ent = m->off_ent; cp.lcap = m->lcap; cp.heap = m->dev_heap; cp.heap_cap = m->heap_cap;
+            cp.heap_used = m->dev_heap_used; cp.colmax = m->dev_colmax; cp.nmax = m->nmax; cp.split_lim = m->split_lim;
+            cp.work_list = nullptr; cp.work_count = nullptr; cp.work_off = 0; cp.work_cap = 0;
+            return cp;
+        };
+        auto launch_compact = [&](const CompactParams &cp, unsigned n_est) -> int {
+            const unsigned cblocks = std::max(1u, std::min<unsigned>((n_est + 7) / 8, (unsigned)m->sm_count * 8));
+            if (vec4) k_compact<4><<<cblocks, 256, 0, st>>>(cp);
+            else if (vec2) k_compact<2><<<cblocks, 256, 0, st>>>(cp);
+            else           k_compact<1><<<cblocks, 256, 0, st>>>(cp);
+            count_launch();
+            QCUDA(cudaPeekAtLastError());
+            return QMANN_OK;
+        };
+        if (!stream_dense) {
+            // records for the whole chunk
+            if (in.dev_ids) {
+                IdsParams ip;
+                ip.ids = in.dev_ids; ip.row_off = in.dev_row_off; ip.ans = in.dev_ans; ip.sen_off = b->dev_sen_off; ip.V = m->cfg.V;
+                ip.story0 = s0; ip.n_stories = n; ip.rec = m->dev_rec; ip.rec_stride = m->rec_stride; ip.off_rend = m->off_rend;
+                ip.off_exc = m->off_exc; ip.off_ent = m->off_ent; ip.lcap = m->lcap; ip.heap = m->dev_heap; ip.heap_cap = m->heap_cap;
+                ip.heap_used = m->dev_heap_used; ip.colmax = m->dev_colmax; ip.nmax = m->nmax; ip.split_lim = m->split_lim;
+                const unsigned cblocks = std::min<unsigned>((n + 7) / 8, (unsigned)m->sm_count * 8);
+                k_ids_compact<<<cblocks, 256, 0, st>>>(ip);
+                count_launch();
+                QCUDA(cudaPeekAtLastError());
+            } else {
+                const int rcc = launch_compact(compact_params(), n);
+                if (rcc) return rcc;
+            }
         }
-        else if (vec4) k_compact<4><<<cblocks, 256, 0, st>>>(cp);
-        else if (vec2) k_compact<2><<<cblocks, 256, 0, st>>>(cp);
-        else           k_compact<1><<<cblocks, 256, 0, st>>>(cp);
-        count_launch();
-        QCUDA(cudaPeekAtLastError());
         if (pe) QCUDA(cudaEventRecord(pe[1], st));
 
         FwdParams p = m->base;
         p.sen_off = b->dev_sen_off; p.story0 = s0; p.n_stories = n; p.n_total = b->N; p.sum_sen = b->sum_sen;
         p.pred = dev_pred; p.h_true = dev_h_true; p.match = dev_match; p.want_h = (dev_h_true != nullptr);
+        p.dm = dev_m; p.dq = dev_q; p.da = dev_a;
+        p.m_bytes = b->sum_sen * (unsigned long long)m->cfg.V * 4ull; p.q_bytes = (unsigned long long)b->N * m->cfg.V * 4ull;
         if (dbg) p.dbg = *dbg;
         int rc;
-        if (!debug && m->fast_ok) {
-            // regular stories in the small fast kernel(s); whatever they decline goes through the general one.
-            // control block: heap_used u64 | counter | slow_count | counter2 | slow_count2 | counter3
+        if (fast) {
+            // regular stories in the production kernel(s); whatever they decline goes through the general one
             if (m->swar_ok) {
                 // packed embedding + scorer first; stories with a row whose column maxima add up above 127 go to the unpacked kernel
                 FwdParams ps = p;
                 ps.img = m->dev_img_swar;
-                ps.tables_bytes = m->tables_fast;
-                ps.slow_list = m->dev_slow_list2; ps.slow_count = m->dev_counter + 3;
-                rc = launch_fast(m, ps, true, st);
+                ps.counter = ctr + CT_PACKED;
+                ps.slow_list = m->dev_slow_list2; ps.slow_count = ctr + CT_LIST2;
+                rc = launch_story(m, ps, true, stream_dense, dump, st);
                 if (rc) return rc;
-                p.work_list = m->dev_slow_list2; p.work_count = m->dev_counter + 3; p.counter = m->dev_counter + 4;
+                p.work_list = m->dev_slow_list2; p.work_count = ctr + CT_LIST2;
             }
-            p.slow_list = m->dev_slow_list; p.slow_count = m->dev_slow_count;
             {
                 FwdParams pf = p;
-                pf.tables_bytes = m->tables_fast;
-                rc = launch_fast(m, pf, false, st);
+                pf.counter = ctr + CT_UNPACKED;
+                pf.slow_list = m->dev_slow_list; pf.slow_count = ctr + CT_LIST1;
+                rc = launch_story(m, pf, false, stream_dense, dump, st);
+                if (rc) return rc;
             }
-            if (rc) return rc;
-            p.work_list = m->dev_slow_list; p.work_count = m->dev_slow_count; p.counter = m->dev_counter2;
+            p.work_list = m->dev_slow_list; p.work_count = ctr + CT_LIST1;
         }
-        rc = launch_forward(m, p, debug, st);
-        if (rc) return rc;
+        // general kernel: everything (instrumented pass) or the declined stories, whose records exist already (record source)
+        // or are made now, chunk_cap at a time (dense stream)
+        const unsigned slices = (fast && stream_dense) ? (n + m->chunk_cap - 1) / m->chunk_cap : 1u;
+        for (unsigned sl = 0; sl < slices; sl++) {
+            FwdParams pg = p;
+            pg.counter = ctr + CT_GENERAL0 + sl;
+            pg.work_off = 0; pg.work_cap = 0xFFFFFFFFu; pg.rec_by_pos = 0;
+            if (fast && stream_dense) {
+                CompactParams cp = compact_params();
+                cp.work_list = m->dev_slow_list; cp.work_count = ctr + CT_LIST1; cp.work_off = sl * m->chunk_cap; cp.work_cap = m->chunk_cap;
+                rc = launch_compact(cp, std::min<unsigned>(n, 4096u));
+                if (rc) return rc;
+                pg.work_off = sl * m->chunk_cap; pg.work_cap = m->chunk_cap; pg.rec_by_pos = 1;
+            }
+            rc = launch_forward(m, pg, dump, st);
+            if (rc) return rc;
+        }
         if (pe) QCUDA(cudaEventRecord(pe[2], st));
     }
     return QMANN_OK;
@@ -672,6 +804,7 @@ int qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, c
     cudaStream_t sc = m->e2e_compute, sx = m->e2e_copy;
     float *dm = m->e2e_m, *dq = m->e2e_q, *da = a_host ? m->e2e_a : nullptr, *dh = (a_host && cost) ? m->e2e_h : nullptr;
     QC2(cudaMemsetAsync(m->e2e_match, 0, sizeof(uint32_t), sc));
+    QC2(cudaMemsetAsync(m->dev_err, 0, sizeof(unsigned), sc));          // every call starts clean (a failed batch does not poison the next)
     // the copy stream runs ahead chunk by chunk; the compute stream waits per chunk, so the H2D of
     // chunk k+1 overlaps the kernels of chunk k
     const uint32_t CH = 4096;
@@ -693,7 +826,7 @@ int qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, c
         FwdInput in;
         in.dev_m = dm; in.dev_q = dq; in.dev_a = da;
         rc = forward_range(m, b, s0, n, in, m->e2e_pred, dh, da ? m->e2e_match : nullptr, nullptr, sc);
-        if (rc) return rc;
+        if (rc) { cudaStreamSynchronize(sx); cudaStreamSynchronize(sc); return rc; }      // nothing of this call stays in flight
     }
     QC2(cudaMemcpyAsync(pred_host, m->e2e_pred, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
     uint32_t mt = 0;
@@ -703,6 +836,7 @@ int qmann_infer_host(qmann_model *m, const float *m_host, const float *q_host, c
     unsigned err = 0;
     QC2(cudaMemcpyAsync(&err, m->dev_err, sizeof(unsigned), cudaMemcpyDeviceToHost, sc));
     QC2(cudaStreamSynchronize(sc));
+    if (err) QC2(cudaMemset(m->dev_err, 0, sizeof(unsigned)));
 #undef QC2
     if (match) *match = mt;
     if (cost && dh) {
@@ -753,6 +887,7 @@ int qmann_infer_ids_host(qmann_model *m, const uint16_t *ids_host, const uint32_
     cudaStream_t sc = m->e2e_compute, sx = m->e2e_copy;
     float *dh = (ans_host && cost) ? m->e2e_h2 : nullptr;
     QC2(cudaMemsetAsync(m->e2e_match, 0, sizeof(uint32_t), sc));
+    QC2(cudaMemsetAsync(m->dev_err, 0, sizeof(unsigned), sc));
     // same pipeline as qmann_infer_host: the copy stream runs ahead chunk by chunk
     const uint32_t CH = 8192;
     size_t ev_i = 0;
@@ -774,7 +909,7 @@ int qmann_infer_ids_host(qmann_model *m, const uint16_t *ids_host, const uint32_
         FwdInput in;
         in.dev_ids = m->ids_dev; in.dev_row_off = m->rowoff_dev; in.dev_ans = ans_host ? m->ans_dev : nullptr;
         rc = forward_range(m, b, s0, n, in, m->e2e_pred2, dh, ans_host ? m->e2e_match : nullptr, nullptr, sc);
-        if (rc) return rc;
+        if (rc) { cudaStreamSynchronize(sx); cudaStreamSynchronize(sc); return rc; }
     }
     QC2(cudaMemcpyAsync(pred_host, m->e2e_pred2, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
     uint32_t mt = 0;
@@ -801,24 +936,45 @@ int qmann_profile_enable(qmann_model *m, int enable)
     if (!m) return fail(QMANN_E_ARG, "null model");
     m->profile = enable != 0;
     m->prof_used = 0;
+    m->prof_acc_c = m->prof_acc_f = 0.0;
+    m->prof_pairs = 0;
     return QMANN_OK;
 }
 
 int qmann_profile_read(qmann_model *m, float *ms_compact, float *ms_forward, uint32_t *n_pairs)
 {
     if (!m) return fail(QMANN_E_ARG, "null model");
-    double tc = 0.0, tf = 0.0;
-    for (size_t i = 0; i + 3 <= m->prof_used; i += 3) {
-        float a = 0.f, b2 = 0.f;
-        QCUDA(cudaEventSynchronize(m->prof_events[i + 2]));
-        QCUDA(cudaEventElapsedTime(&a, m->prof_events[i], m->prof_events[i + 1]));
-        QCUDA(cudaEventElapsedTime(&b2, m->prof_events[i + 1], m->prof_events[i + 2]));
-        tc += a; tf += b2;
-    }
-    if (ms_compact) *ms_compact = (float)tc;
-    if (ms_forward) *ms_forward = (float)tf;
-    if (n_pairs) *n_pairs = (uint32_t)(m->prof_used / 3);
-    m->prof_used = 0;
+    const int rc = profile_fold(m);
+    if (rc) return rc;
+    if (ms_compact) *ms_compact = (float)m->prof_acc_c;
+    if (ms_forward) *ms_forward = (float)m->prof_acc_f;
+    if (n_pairs) *n_pairs = (uint32_t)m->prof_pairs;
+    m->prof_acc_c = m->prof_acc_f = 0.0;
+    m->prof_pairs = 0;
+    return QMANN_OK;
+}
+
+int qmann_check_errors(qmann_model *m, void *stream, uint32_t *flags)
+{
+    if (!m) return fail(QMANN_E_ARG, "null model");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned err = 0;
+    QCUDA(cudaMemcpyAsync(&err, m->dev_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    QCUDA(cudaStreamSynchronize(st));
+    if (err) QCUDA(cudaMemset(m->dev_err, 0, sizeof(unsigned)));
+    if (flags) *flags = err;
+    return QMANN_OK;
+}
+
+int qmann_path_counts(qmann_model *m, void *stream, uint64_t tiers[3])
+{
+    if (!m || !tiers) return fail(QMANN_E_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    QCUDA(cudaMemcpyAsync(h, m->dev_path_count, sizeof(h), cudaMemcpyDeviceToHost, st));
+    QCUDA(cudaMemsetAsync(m->dev_path_count, 0, sizeof(h), st));
+    QCUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 3; i++) tiers[i] = h[i];
     return QMANN_OK;
 }
 

@@ -37,6 +37,20 @@ struct CompactParams {
     unsigned long long *heap_used;
     const unsigned char *colmax;       // [V] max |code| of a column over all embedding tables and dims
     unsigned nmax;                     // largest count n with n * 2^frac_w representable in every weight format (0: no splitting)
+    unsigned split_lim;                // min over the hops of the weight-format code limit lw[h]: n copies of a unit entry equal the
+                                       // reference's per-product clamp Q_w(Q_w(n) * Q_w(T)) only while n * max|code| <= lw[h] for every hop
+    const unsigned *work_list;         // optional: chunk indices of the stories to compact (NULL: all of the chunk); the launch
+    const unsigned *work_count;        // handles list positions work_off .. work_off + work_cap and writes record (position - work_off)
+    unsigned work_off, work_cap;
+};
+
+// Scratch layout and shared-memory image of the production kernel k_story (qmann_fast.cuh); byte offsets.
+struct FastLayout {
+    unsigned sA[MAXH], sCM, sTAU, sW8;     // shared-memory image: A_h tables, packed column maxima, tau, int8 image of W
+    unsigned tables_bytes;
+    unsigned warp_bytes, LW;               // per-warp scratch; capacity of the entry list (16-bit premultiplied offsets)
+    unsigned o_rend, o_sc, o_ex, o_pq, o_uvec, o_ub32, o_ovec, o_ufl, o_zent, o_brow, o_perm, o_cnt, o_bar, o_stage;
+    unsigned NB, R, buf_bytes;             // dense stream: staging buffers per warp, rows per chunk, bytes per buffer
 };
 
 struct FwdParams {
@@ -77,11 +91,22 @@ struct FwdParams {
     // slow_list; the general kernel then takes its work from work_list[0 .. *work_count)
     unsigned *slow_list, *slow_count;
     const unsigned *work_list, *work_count;
+    unsigned work_off, work_cap;           // general kernel: list positions work_off .. work_off + work_cap of work_list
+    unsigned rec_by_pos;                   // general kernel: record index = list position - work_off (else the chunk index)
     // linear-map product table (global, L2-resident): lut[offL[h] + (j*255 + v + 127)*DP + i] =
     // Q_w(Q_w(Hm[i][j]) * v) for every code v of Q_bin(u[j]); NULL: compute the products (large d)
     const signed char *lut;
     unsigned offL[MAXH];
     qmann_debug dbg;
+    // ---- production kernel k_story ----
+    FastLayout fl;
+    const float *dm, *dq, *da;             // dense arenas (DENSE source): streamed by the kernel itself with bulk copies
+    unsigned long long m_bytes, q_bytes;   // their sizes in bytes (copies never read past them)
+    const unsigned char *colmax;           // count splitting, as in CompactParams
+    unsigned nmax, split_lim;
+    int fast_softmax;                      // attention codes from a float total when no weight is near a truncation boundary
+    unsigned pf_dist, pf_mode;             // L2 prefetch of the story pf_dist claims ahead (0: off, 1: bulk prefetch, 2: per line)
+    unsigned long long *path_count;        // [3] stories that entered the packed, unpacked and general tier
 };
 
 // =============================================================================================
@@ -278,7 +303,7 @@ __device__ __forceinline__ unsigned emit_general(const CompactParams &p, const f
             if (bnu) {                           // some lane holds a value that is not 1.0
                 if (had && !unit) {
                     const float n = truncf(x);
-                    if (n == x && x >= 2.0f && x <= (float)p.nmax && (unsigned)n * (unsigned)p.colmax[col] <= 127u) rep = (unsigned)n - 1u;
+                    if (n == x && x >= 2.0f && x <= (float)p.nmax && (unsigned)n * (unsigned)p.colmax[col] <= p.split_lim) rep = (unsigned)n - 1u;
                     else is_exc = true;
                 }
                 const unsigned bex = __ballot_sync(0xffffffffu, is_exc);
@@ -408,11 +433,14 @@ __global__ void __launch_bounds__(256) k_compact(const CompactParams p)
 {
     const unsigned lane = threadIdx.x & 31;
     const unsigned warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < p.n_stories; w += warps) {
+    unsigned n_work = p.n_stories;
+    if (p.work_list) { const unsigned c = *p.work_count; n_work = (c > p.work_off) ? min(c - p.work_off, p.work_cap) : 0u; }
+    for (unsigned wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < n_work; wi += warps) {
+        const unsigned w = p.work_list ? p.work_list[p.work_off + wi] : wi;
         const unsigned story = p.story0 + w;
         const unsigned long long soff = p.sen_off[story];
         const unsigned S = (unsigned)(p.sen_off[story + 1] - soff);
-        unsigned char *rec = p.rec + (size_t)w * p.rec_stride;
+        unsigned char *rec = p.rec + (size_t)wi * p.rec_stride;
         unsigned *hdr = reinterpret_cast<unsigned *>(rec);
         unsigned short *rend = reinterpret_cast<unsigned short *>(rec + p.off_rend);
         uint2 *exc = reinterpret_cast<uint2 *>(rec + p.off_exc);
@@ -481,7 +509,7 @@ struct IdsParams {
     unsigned long long heap_cap;
     unsigned long long *heap_used;
     const unsigned char *colmax;
-    unsigned nmax;
+    unsigned nmax, split_lim;
 };
 
 // Classification and emission of the (row, id) occurrences held one per lane (`have` lanes, in row-major order).
@@ -498,7 +526,7 @@ __device__ __forceinline__ unsigned ids_emit(const IdsParams &p, bool have, unsi
     const bool ok = have && !oob;
     unsigned bl;
     if (MODE == 0) {
-        const bool unit = ok && (cnt == 1u || (cnt <= p.nmax && cnt * (unsigned)p.colmax[id] <= 127u));
+        const bool unit = ok && (cnt == 1u || (cnt <= p.nmax && cnt * (unsigned)p.colmax[id] <= p.split_lim));
         const bool isx = ok && !unit && !earlier;
         bl = __ballot_sync(0xffffffffu, unit);
         const unsigned pos = base + __popc(bl & lt);
@@ -808,8 +836,10 @@ __global__ void __launch_bounds__(512, 1) k_forward(const __grid_constant__ FwdP
     constexpr int G = 32 / LPR;                 // rows embedded concurrently by one warp
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned g = lane / LPR, q = lane % LPR;
-    const unsigned n_work = p.work_count ? *p.work_count : p.n_stories;
+    unsigned n_work = p.n_stories;
+    if (p.work_count) { const unsigned c = *p.work_count; n_work = (c > p.work_off) ? min(c - p.work_off, p.work_cap) : 0u; }
     if (n_work == 0) return;                    // nothing left over by the fast kernel
+    if (p.path_count && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.path_count + 2, (unsigned long long)n_work);       // stories entering the general tier
 
     // ---- stage the quantised tables into shared memory (once per CTA) ----
     {
@@ -850,13 +880,14 @@ __global__ void __launch_bounds__(512, 1) k_forward(const __grid_constant__ FwdP
         if (lane == 0) w = atomicAdd(p.counter, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= n_work) break;
-        if (p.work_list) w = p.work_list[w];
+        const unsigned pos = w;
+        if (p.work_list) w = p.work_list[p.work_off + pos];
         const unsigned story = p.story0 + w;
         const unsigned long long soff = p.sen_off[story];
         const unsigned S = (unsigned)(p.sen_off[story + 1] - soff);
 
         // ---- load this story's compact record ----
-        const unsigned char *rec = p.rec + (size_t)w * p.rec_stride;
+        const unsigned char *rec = p.rec + (size_t)(p.rec_by_pos ? pos : w) * p.rec_stride;
         const unsigned *hdr = reinterpret_cast<const unsigned *>(rec);
         const unsigned n_ent = hdr[0], flags = hdr[1], ans_idx = hdr[2], heap_off = hdr[3], n_exc = hdr[4];
         if (flags & FLAG_ERROR) {
@@ -1015,6 +1046,7 @@ __global__ void __launch_bounds__(512, 1) k_forward(const __grid_constant__ FwdP
                     // Q_f(p) inside the weighted read                               layer_cuda.cu:561
                     code = (unsigned)qi_encode(pr, p.iff[h], ff);
                     if (DEBUG && p.dbg.dev_p) p.dbg.dev_p[(size_t)h * p.sum_sen + soff + r] = pr;
+                    if (DEBUG && p.dbg.dev_pcode) p.dbg.dev_pcode[(size_t)h * p.sum_sen + soff + r] = (unsigned char)code;
                 }
                 // compact the slots whose quantised weight is non-zero: the rest contribute
                 // Q(0 * c) = 0 to every output dimension
@@ -1144,6 +1176,7 @@ __global__ void __launch_bounds__(512, 1) k_forward(const __grid_constant__ FwdP
                     zbuf[i] = z[k];
                     zmax = fmaxf(zmax, z[k]);
                     if (DEBUG && p.dbg.dev_z) p.dbg.dev_z[(size_t)story * V + i] = z[k];
+                    if (DEBUG && p.dbg.dev_cand) p.dbg.dev_cand[(size_t)story * V + i] = 2;
                 }
             }
         }
@@ -1197,6 +1230,7 @@ __global__ void __launch_bounds__(512, 1) k_forward(const __grid_constant__ FwdP
             if (p.pred) p.pred[story] = pred_i;
             if (p.h_true) p.h_true[story] = h_true_v;
             if (p.match && ans_idx != ANS_NONE && pred_i == ans_idx) atomicAdd(p.match, 1u);
+            if (DEBUG && p.dbg.dev_path) p.dbg.dev_path[story] = 3;
         }
         __syncwarp();
     }

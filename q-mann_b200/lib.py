@@ -33,7 +33,8 @@ class QWeights(C.Structure):
 
 
 class QDebug(C.Structure):
-    _fields_ = [(f"dev_{k}", _FP) for k in ("u0", "M", "C", "s", "p", "o", "g", "u", "z", "h")]
+    _fields_ = [(f"dev_{k}", _FP) for k in ("u0", "M", "C", "s", "p", "o", "g", "u", "z", "h", "pcode", "path", "cand")] + \
+               [("production", _U32)]
 
 
 def build(force: bool = False, extra: str = "") -> str:
@@ -81,6 +82,10 @@ def lib() -> C.CDLL:
     L.qmann_infer_ids_host.restype = C.c_int
     L.qmann_infer_ids_host.argtypes = [C.c_void_p, _FP, _FP, _FP, C.POINTER(_U32), _U32, C.POINTER(_U32), C.POINTER(_U32),
                                        C.POINTER(C.c_float)]
+    L.qmann_check_errors.restype = C.c_int
+    L.qmann_check_errors.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_U32)]
+    L.qmann_path_counts.restype = C.c_int
+    L.qmann_path_counts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     L.qmann_profile_enable.restype = C.c_int
     L.qmann_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.qmann_profile_read.restype = C.c_int
@@ -186,25 +191,46 @@ class Model:
         _check(lib().qmann_profile_read(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return float(a.value), float(b.value), int(n.value)
 
+    def check_errors(self, stream=None) -> int:
+        """Device-side error flag of the asynchronous entries (qmann_check_errors): synchronises, returns and clears it."""
+        sptr = stream.cuda_stream if stream is not None else self.torch.cuda.current_stream().cuda_stream
+        f = _U32(0)
+        _check(lib().qmann_check_errors(self._h, C.c_void_p(sptr), C.byref(f)))
+        return int(f.value)
+
+    def path_counts(self, stream=None):
+        """Stories that entered the (packed, unpacked, general) tier since the last call (qmann_path_counts)."""
+        sptr = stream.cuda_stream if stream is not None else self.torch.cuda.current_stream().cuda_stream
+        t = (C.c_uint64 * 3)()
+        _check(lib().qmann_path_counts(self._h, C.c_void_p(sptr), t))
+        return int(t[0]), int(t[1]), int(t[2])
+
     # ---- device-resident batch ---------------------------------------------------------------
     def upload(self, st) -> "DeviceBatch":
         return DeviceBatch(self, st)
 
     def forward(self, db: "DeviceBatch", with_answers: bool = True, want_h: bool = False, debug: bool = False,
-                stream=None) -> Dict[str, object]:
-        """One pass of the hot path over the whole device-resident batch (asynchronous)."""
+                stream=None, production_dump: bool = False) -> Dict[str, object]:
+        """One pass of the hot path over the whole device-resident batch (asynchronous).
+        debug: every story through the instrumented general kernel, all intermediates returned.
+        production_dump: the production kernels (k_story tiers + general kernel for what they decline) with their dump
+        instantiations: u0, s, pcode (Q_f(p) codes = selected slots), o, g, u, z (exact rows), cand, path."""
         torch = self.torch
         N, H, d, V, ss = db.N, self.cfg.H, self.cfg.d, self.cfg.V, db.sum_sen
         out: Dict[str, object] = {}
         out["pred"] = db.pred
         db.match.zero_()
         dbg = None
-        if debug:
+        if debug or production_dump:
             dbg = QDebug()
+            dbg.production = 1 if production_dump else 0
             shapes = dict(u0=(N, d), M=(H, ss, d), C=(H, ss, d), s=(H, ss), p=(H, ss), o=(H, N, d), g=(H, N, d), u=(H, N, d),
                           z=(N, V), h=(N, V))
             for k, shp in shapes.items():
                 out[k] = torch.zeros(shp, dtype=torch.float32, device=self.device)
+                setattr(dbg, f"dev_{k}", out[k].data_ptr())
+            for k, shp in dict(pcode=(H, ss), path=(N,), cand=(N, V)).items():
+                out[k] = torch.zeros(shp, dtype=torch.uint8, device=self.device)
                 setattr(dbg, f"dev_{k}", out[k].data_ptr())
         sptr = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
         if getattr(db, "ids", None) is not None:

@@ -36,10 +36,11 @@ class ModelConfig:
     iwl: int = 5                # argv[4]; run.sh:18 passes 5 => base format (5,2)
     en_mq: bool = True          # EN_MQ, define.h:79
     V_dict: int = 0             # dictionary size (incl. NULL at 0); time columns are V_dict..V-1
+    wl: int = BW_WL             # word length BW_WL (define.h:21); < 8 gives formats narrower than a byte
 
     def formats(self) -> Dict[str, List[int]]:
         """Per-hop (iwl, frac) arrays exactly as MemN2N.c:714-775 computes them."""
-        frac = BW_WL - 1 - self.iwl
+        frac = self.wl - 1 - self.iwl
         iwl = [self.iwl] * self.H
         fr = [frac] * self.H
         iwl_w, frac_w = list(iwl), list(fr)
