@@ -624,7 +624,9 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
     const bool vec2 = (m->cfg.V % 2 == 0) && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 8 == 0);
     const bool fast = production && m->fast_ok && m->NW_fast > 0;
     const char *env_stream = getenv("QMANN_DENSE_STREAM");
-    const bool stream_dense = fast && !in.dev_ids && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 16 == 0) && !(env_stream && atoi(env_stream) == 0);
+    // k_story's own bulk-copy stream + in-kernel compaction measured slower than k_compact followed by the record tiers
+    // (0.66 vs 0.53 ms on C2, profiles/r02_k_story_dense_stream.txt): opt-in only
+    const bool stream_dense = fast && !in.dev_ids && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 16 == 0) && (env_stream && atoi(env_stream) == 1);
     const uint32_t cap = stream_dense ? m->story_chunk_cap : m->chunk_cap;
     unsigned *ctr = m->dev_counter;
     for (uint32_t s0 = first; s0 < first + count; s0 += cap) {
