@@ -26,6 +26,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <time.h>
+#include <unistd.h>
 
 using namespace qmann;
 
@@ -48,6 +50,7 @@ void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxe
 
 #include "qmann_kernels.cuh"
 #include "qmann_fast.cuh"
+#include "qmann_tcstory.cuh"
 
 namespace {
 
@@ -93,6 +96,11 @@ struct qmann_model {
     bool fast_ok = false;                    // every weight format has an integer bit (Q_w(1.0) = 2^frac_w)
     unsigned char *dev_colmax = nullptr;     // [V] max |code| per column over all embedding tables (count splitting)
     unsigned nmax = 0, split_lim = 127;
+    // tensor-core tier (k_story_tc): fp32 image of the A_h tables [160][V] for the tf32 MMA, its tensor map, geometry
+    float *dev_tc_tab = nullptr;
+    bool tc_ok = false;
+    CUtensorMap tc_tmT;
+    unsigned tc_kch = 0, tc_teams = 0, tc_smem = 0;
     // qmann_infer_host staging (grow-only device arenas, two streams)
     float *e2e_m = nullptr, *e2e_q = nullptr, *e2e_a = nullptr, *e2e_h = nullptr;
     uint32_t *e2e_pred = nullptr, *e2e_match = nullptr;
@@ -206,10 +214,87 @@ int launch_story(const qmann_model *m, const FwdParams &p, bool swar, bool dense
 {
     return dense ? launch_story_d<true>(m, p, swar, dump, st) : launch_story_d<false>(m, p, swar, dump, st);
 }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tmap_encode_fn tmap_encoder()
+{
+    static tmap_encode_fn fn = []() -> tmap_encode_fn {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+        return (tmap_encode_fn)f;
+    }();
+    return fn;
+}
+// fp32 matrix [rows][cols] (row pitch cols * 4, a multiple of 16 bytes), boxes of 32 columns x box_rows rows, 128-byte swizzle
+bool tmap_rows_f32(CUtensorMap *out, const void *base, unsigned long long rows, unsigned cols, unsigned box_rows)
+{
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc || rows == 0) return false;
+    cuuint64_t dims[2] = {cols, rows}, strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {32, box_rows}, es[2] = {1, 1};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+#ifdef QMANN_TC_TRACE
+unsigned *g_tc_trace = nullptr;
+unsigned g_tc_trace_blocks = 0, g_tc_trace_warps = 0;
+#endif
+// k_story_tc over the whole chunk (dense arenas, every story <= 64 sentences); declined stories -> p.slow_list
+int launch_story_tc(const qmann_model *m, const FwdParams &p, const float *dev_m, unsigned long long total_rows, bool dump, cudaStream_t st)
+{
+    TcParams tp;
+    memset(&tp, 0, sizeof(tp));
+    if (!tmap_rows_f32(&tp.tmX, dev_m, total_rows, m->cfg.V, 32)) return fail(QMANN_E_CUDA, "cuTensorMapEncodeTiled failed for the sentence arena");
+    tp.tmT = m->tc_tmT;
+    tp.f = p;
+    tp.n_groups = (p.n_stories + 3) / 4;
+    tp.total_rows = (unsigned)total_rows;
+    tp.kch = m->tc_kch;
+    tp.n_teams = m->tc_teams;
+    const unsigned grid = (unsigned)std::min<unsigned>((unsigned)m->sm_count, tp.n_groups);
+    const unsigned block = TC_WARPS * 32;
+#ifdef QMANN_TC_TRACE
+    if (!g_tc_trace) QCUDA(cudaHostAlloc((void **)&g_tc_trace, 148 * 24 * 16, cudaHostAllocMapped));
+    memset(g_tc_trace, 0, 148 * 24 * 16);
+    { unsigned *dp = nullptr; QCUDA(cudaHostGetDevicePointer((void **)&dp, g_tc_trace, 0)); tp.trace = dp; }
+    g_tc_trace_blocks = grid; g_tc_trace_warps = block / 32;
+#endif
+    static bool attr_done[2] = {false, false};
+    if (dump) {
+        if (!attr_done[1]) { QCUDA(cudaFuncSetAttribute(k_story_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->max_smem)); attr_done[1] = true; }
+        k_story_tc<true><<<grid, block, m->tc_smem, st>>>(tp);
+    } else {
+        if (!attr_done[0]) { QCUDA(cudaFuncSetAttribute(k_story_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->max_smem)); attr_done[0] = true; }
+        k_story_tc<false><<<grid, block, m->tc_smem, st>>>(tp);
+    }
+    count_launch();
+    QCUDA(cudaPeekAtLastError());
+    return QMANN_OK;
+}
 }  // namespace
 
 extern "C" {
 
+#ifdef QMANN_TC_TRACE
+// debug builds only: where every warp of the last k_story_tc launch stands (CTAs that have not reached the end)
+void qmann_tc_trace_dump(void)
+{
+    if (!g_tc_trace) return;
+    for (unsigned b = 0; b < g_tc_trace_blocks; b++) {
+        const unsigned *t = g_tc_trace + (size_t)b * 24 * 4;
+        bool done = true;
+        for (unsigned w = 0; w < g_tc_trace_warps; w++) done = done && (t[4 * w] == 0xE0Du);
+        if (done) continue;
+        fprintf(stderr, "CTA %u\n", b);
+        for (unsigned w = 0; w < g_tc_trace_warps; w++) fprintf(stderr, "  warp %2u: %08x %08x %08x %08x\n", w, t[4 * w], t[4 * w + 1], t[4 * w + 2], t[4 * w + 3]);
+    }
+    fflush(stderr);
+}
+#endif
 const char *qmann_last_error(void) { return g_err.c_str(); }
 const char *qmann_version(void) { return "qmann_b200 0.1 (sm_100a)"; }
 uint64_t qmann_launch_count(void) { return g_launches.load(); }
@@ -487,6 +572,27 @@ static int model_build(qmann_model *m, const qmann_config *cfg, const qmann_weig
         if (const char *e = getenv("QMANN_PF_MODE")) p.pf_mode = (unsigned)std::max(0, atoi(e));
         if (p.pf_dist == 0) p.pf_mode = 0;
     }
+    // ---- tensor-core tier: dense rows x A_h tables on tcgen05 (k_story_tc) ----
+    {
+        const char *env_tc = getenv("QMANN_TC");
+        const unsigned kch = (c.V + 31) / 32;
+        bool ok = m->swar_ok && c.H <= 3 && c.d <= TC_HCOLS && DP == 64 && c.V % 4 == 0 && c.V <= 256 && (!c.lin_map || p.lut) && c.S_max >= 1 &&
+                  (env_tc && atoi(env_tc) == 1) && tmap_encoder() != nullptr;      // opt-in until it beats the two-kernel path
+        unsigned teams = TC_MAX_TEAMS;
+        if (const char *e = getenv("QMANN_TC_TEAMS")) teams = (unsigned)std::min<int>(TC_MAX_TEAMS, std::max(1, atoi(e)));
+        unsigned need = 0;
+        for (; ok && teams >= 1; teams--) {
+            need = kch * TC_TABCH_BYTES + TC_NSTAGE * TC_STAGE_BYTES + TCB_BYTES + 4 * teams * TW_BYTES + 1024;
+            if (need <= (unsigned)max_smem) break;
+        }
+        if (ok && teams >= 1) {
+            QCUDA(cudaMalloc((void **)&m->dev_tc_tab, (size_t)TC_NT * c.V * sizeof(float)));
+            k_prep_tc<<<64, 256>>>(m->dev_img, m->dev_tc_tab, c.V, c.d, DP, c.H, p.offA[0], c.H > 1 ? p.offA[1] : 0, c.H > 2 ? p.offA[2] : 0);
+            count_launch();
+            ok = tmap_rows_f32(&m->tc_tmT, m->dev_tc_tab, TC_NT, c.V, TC_NT);
+            m->tc_ok = ok; m->tc_kch = kch; m->tc_teams = teams; m->tc_smem = need;
+        }
+    }
     QCUDA(cudaPeekAtLastError());
     QCUDA(cudaDeviceSynchronize());
     p.img = m->dev_img;
@@ -519,6 +625,7 @@ static int model_build(qmann_model *m, const qmann_config *cfg, const qmann_weig
 void qmann_model_destroy(qmann_model *m)
 {
     if (!m) return;
+    cudaFree(m->dev_tc_tab);
     cudaFree(m->dev_img); cudaFree(m->dev_lut); cudaFree(m->dev_rec); cudaFree(m->dev_heap); cudaFree(m->dev_heap_used);
     cudaFree(m->dev_path_count); cudaFree(m->dev_slow_list); cudaFree(m->dev_slow_list2); cudaFree(m->dev_img_swar); cudaFree(m->dev_err); cudaFree(m->dev_colmax);
     if (m->host_batch) qmann_batch_destroy(m->host_batch);
@@ -626,7 +733,10 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
     const char *env_stream = getenv("QMANN_DENSE_STREAM");
     // k_story's own bulk-copy stream + in-kernel compaction measured slower than k_compact followed by the record tiers
     // (0.66 vs 0.53 ms on C2, profiles/r02_k_story_dense_stream.txt): opt-in only
-    const bool stream_dense = fast && !in.dev_ids && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 16 == 0) && (env_stream && atoi(env_stream) == 1);
+    const bool aligned16 = !in.dev_ids && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 16 == 0);
+    // first tier on the tensor cores (k_story_tc): dense arenas, stories of at most 64 sentences
+    const bool use_tc = fast && m->tc_ok && aligned16 && b->max_sen <= 64 && b->sum_sen > 0 && b->sum_sen < 0x7FFFFFFFull;
+    const bool stream_dense = use_tc || (fast && aligned16 && (env_stream && atoi(env_stream) == 1));
     const uint32_t cap = stream_dense ? m->story_chunk_cap : m->chunk_cap;
     unsigned *ctr = m->dev_counter;
     for (uint32_t s0 = first; s0 < first + count; s0 += cap) {
@@ -688,7 +798,14 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
         int rc;
         if (fast) {
             // regular stories in the production kernel(s); whatever they decline goes through the general one
-            if (m->swar_ok) {
+            if (use_tc) {
+                FwdParams ps = p;
+                ps.counter = ctr + CT_PACKED;
+                ps.slow_list = m->dev_slow_list2; ps.slow_count = ctr + CT_LIST2;
+                rc = launch_story_tc(m, ps, dev_m, b->sum_sen, dump, st);
+                if (rc) return rc;
+                p.work_list = m->dev_slow_list2; p.work_count = ctr + CT_LIST2;
+            } else if (m->swar_ok) {
                 // packed embedding + scorer first; stories with a row whose column maxima add up above 127 go to the unpacked kernel
                 FwdParams ps = p;
                 ps.img = m->dev_img_swar;

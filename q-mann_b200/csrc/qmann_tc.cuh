@@ -107,6 +107,11 @@ __device__ __forceinline__ void tmem_st4(unsigned taddr, const unsigned (&v)[4])
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
 
+__device__ __forceinline__ void tmem_st1(unsigned taddr, unsigned v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+
 // ---- tcgen05.mma, kind::tf32, both operands from shared memory (K-major, 128-byte swizzle) ----
 // Shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes apart inside 8-row groups of 1024 bytes
 // (exactly what a TMA box of 32 fp32 columns with CU_TENSOR_MAP_SWIZZLE_128B writes): start address >> 4 in bits 0-13,
