@@ -258,8 +258,8 @@ int launch_story_tc(const qmann_model *m, const FwdParams &p, const float *dev_m
     const unsigned grid = (unsigned)std::min<unsigned>((unsigned)m->sm_count, tp.n_groups);
     const unsigned block = TC_WARPS * 32;
 #ifdef QMANN_TC_TRACE
-    if (!g_tc_trace) QCUDA(cudaHostAlloc((void **)&g_tc_trace, 148 * 24 * 16, cudaHostAllocMapped));
-    memset(g_tc_trace, 0, 148 * 24 * 16);
+    if (!g_tc_trace) QCUDA(cudaHostAlloc((void **)&g_tc_trace, 2 * 148 * 24 * 16, cudaHostAllocMapped));
+    memset(g_tc_trace, 0, 2 * 148 * 24 * 16);
     { unsigned *dp = nullptr; QCUDA(cudaHostGetDevicePointer((void **)&dp, g_tc_trace, 0)); tp.trace = dp; }
     g_tc_trace_blocks = grid; g_tc_trace_warps = block / 32;
 #endif
@@ -284,6 +284,12 @@ extern "C" {
 void qmann_tc_trace_dump(void)
 {
     if (!g_tc_trace) return;
+    // clock accumulators (units of 16 cycles) of CTAs 0 and 1, four per warp (meaning per role, see qmann_tcstory.cuh)
+    for (unsigned b = 0; b < 2 && b < g_tc_trace_blocks; b++) {
+        const unsigned *t = g_tc_trace + 148 * 24 * 4 + (size_t)b * 24 * 4;
+        fprintf(stderr, "CTA %u clocks/16\n", b);
+        for (unsigned w = 0; w < g_tc_trace_warps; w++) fprintf(stderr, "  warp %2u: %9u %9u %9u %9u\n", w, t[4 * w], t[4 * w + 1], t[4 * w + 2], t[4 * w + 3]);
+    }
     for (unsigned b = 0; b < g_tc_trace_blocks; b++) {
         const unsigned *t = g_tc_trace + (size_t)b * 24 * 4;
         bool done = true;

@@ -14,8 +14,8 @@
 //   warp 16       producer: claims groups of four stories, issues the TMA boxes (32 rows x 32 columns) of every K chunk
 //   warp 17       issues the MMAs: M = 128 rows (rows 32t..32t+31 of the four stories, one story per 32-lane quadrant of tensor
 //                 memory), N = 160 (3 hops x 52 dims + the three row-bias columns), K = 8 per instruction
-//   warps 18-20   validate the staged rows (every value 0/1, or a count whose n copies of a unit entry are exact), one warp
-//                 per ring stage
+//   warps 18-23   validate the staged rows (every value 0/1, or a count whose n copies of a unit entry are exact); every
+//                 stage is split among the six warps so that it is released quickly
 // Stories this tier does not cover (a row sum beyond a byte, irregular values, very many selected slots) are appended to
 // p.slow_list for the unpacked k_story tier / the general kernel.
 #pragma once
@@ -30,10 +30,11 @@ constexpr unsigned TC_DW = 13;                  // packed words per hop and row
 constexpr unsigned TC_BIAS0 = 156;              // columns 156.. : sum of column maxima per hop
 constexpr unsigned TC_NSTAGE = 3, TC_STAGE_BYTES = 128 * 128, TC_TABCH_BYTES = TC_NT * 128;
 constexpr unsigned TC_NG = 16;                  // group descriptor ring
-constexpr unsigned TC_NVAL = 3;                 // validator warps: one per ring stage (a warp waits only on the barrier it releases)
+constexpr unsigned TC_NVAL = 6;                 // validator warps: each checks a sixth of EVERY stage, so each sees every phase of every
+                                                // full barrier and is one of the arrivals that release it (a barrier can then never lap a waiter)
 constexpr unsigned TC_MAX_TEAMS = 4;
 constexpr unsigned TC_W_PRODUCER = 4 * TC_MAX_TEAMS, TC_W_MMA = TC_W_PRODUCER + 1, TC_W_VAL0 = TC_W_MMA + 1, TC_WARPS = TC_W_VAL0 + TC_NVAL;
-static_assert(TC_NVAL == TC_NSTAGE, "one validator per stage");
+static_assert(TC_WARPS <= 24, "trace layout");
 constexpr unsigned TC_PK_COLS = 40;             // packed slot: 3 hops x 13 words (+1) per row set
 constexpr unsigned TC_NNZ_CAP = 16, TC_ENT_CAP = 160;
 // per-warp scratch (bytes)
@@ -42,7 +43,7 @@ constexpr unsigned TW_SELR = 0, TW_PQ = 16, TW_UVEC = 32, TW_OVEC = 96, TW_SQ = 
 // control block (bytes from its base)
 // (one accumulator-ready barrier per team: a waiter may then never be more than one phase behind its barrier)
 constexpr unsigned TCB_TAB = 0, TCB_FULL = 8, TCB_EMPTY = 32, TCB_DFREE = 56, TCB_TMEM = 64, TCB_DFULL = 96, TCB_GBAR = 128, TCB_GDESC = 256,
-                   TCB_BAD = TCB_GDESC + TC_NG * 48, TCB_BYTES = TCB_BAD + TC_NG * 4;
+                   TCB_BAD = TCB_GDESC + TC_NG * 48, TCB_TAU = TCB_BAD + TC_NG * 4, TCB_BYTES = TCB_TAU + 128;
 
 struct TcGroup {
     unsigned story[4];        // chunk index of the story in each quadrant (0xFFFFFFFF: empty)
@@ -62,19 +63,30 @@ struct alignas(64) TcParams {
     volatile unsigned *trace;  // QMANN_TC_TRACE builds: mapped host memory, 4 progress words per warp of CTA 0
 };
 #ifdef QMANN_TC_TRACE
+#if QMANN_TC_TRACE == 2
+#define TCT(slot, val) do { } while (0)          /* clock accounting only */
+#else
 #define TCT(slot, val) do { if (tp.trace && (threadIdx.x & 31) == 0) { tp.trace[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 4 + (slot)] = (val); } } while (0)
+#endif
+#define TCK_DECL unsigned long long tck_acc[4] = {0ull, 0ull, 0ull, 0ull}; long long tck_t = clock64();
+#define TCK(slot) do { const long long n_ = clock64(); tck_acc[slot] += (unsigned long long)(n_ - tck_t); tck_t = n_; } while (0)
+#define TCK_FLUSH do { if (tp.trace && (threadIdx.x & 31) == 0) for (int i_ = 0; i_ < 4; i_++) tp.trace[148 * 24 * 4 + (blockIdx.x * 24 + (threadIdx.x >> 5)) * 4 + i_] = (unsigned)(tck_acc[i_] >> 4); } while (0)
 #else
 #define TCT(slot, val) do { } while (0)
+#define TCK_DECL
+#define TCK(slot) do { } while (0)
+#define TCK_FLUSH do { } while (0)
 #endif
 
 // One staged K chunk (128 rows x 32 columns): every value must be 0.0 or 1.0, or an integer count n in 2..nmax whose n copies
 // of the unit entry are exact in every table (n * colmax <= split_lim); otherwise the story is marked for the next tier.
 __device__ __forceinline__ void tc_validate_stage(const FwdParams &p, const unsigned char *stage, unsigned t, unsigned k, const TcGroup *gd,
-                                                  unsigned char *bad, unsigned lane)
+                                                  unsigned char *bad, unsigned lane, unsigned v)
 {
+    // the stage is 32 groups of four rows (one 128-bit load per lane covers a group); validator v takes groups v, v + NVAL, ...
     const unsigned pc = lane & 7u;
-#pragma unroll 2
-    for (unsigned i0 = 0; i0 < 32; i0 += 2) {
+#pragma unroll 1
+    for (unsigned i0 = 2u * v; i0 < 32; i0 += 2u * TC_NVAL) {
         const unsigned r0 = 4u * i0 + (lane >> 3), r1 = r0 + 4u;
         const float4 a = *reinterpret_cast<const float4 *>(stage + r0 * 128u + pc * 16u);
         const float4 b = *reinterpret_cast<const float4 *>(stage + r1 * 128u + pc * 16u);
@@ -112,68 +124,57 @@ __device__ __forceinline__ void tc_validate_stage(const FwdParams &p, const unsi
     }
 }
 
-// Scan one dense row in global memory (V % 4 == 0, 16-byte aligned) and append its entries (column * DP) to ent[].
-__device__ __forceinline__ unsigned tc_scan_row_g(const FwdParams &p, const float *__restrict__ rowp, unsigned short *__restrict__ ent, unsigned cap,
-                                                  unsigned base, unsigned lane, bool &irregular)
+// One dense row in global memory (V <= 256, V % 4 == 0, 16-byte aligned): lane l loads float4 l and l + 32 ...
+__device__ __forceinline__ void tc_row_load(const FwdParams &p, const float *__restrict__ rowp, unsigned lane, float (&v)[8])
 {
-    const unsigned lt = (1u << lane) - 1u;
     const float4 *b4 = reinterpret_cast<const float4 *>(rowp);
     const unsigned n4 = p.V >> 2;
-    for (unsigned c0 = 0; c0 < n4; c0 += 64) {
-        const unsigned ca = c0 + lane, cb = ca + 32u;
-        float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = 0.0f;
-        if (ca < n4) { const float4 t = ldg_stream4(b4 + ca); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-        if (cb < n4) { const float4 t = ldg_stream4(b4 + cb); v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w; }
-        if (!chunk_irregular<4>(v)) base = emit_units_s(unit_mask<4>(v), ca, cb, 0u, p.DP, ent, cap, base, lt);
-        else base = emit_general_s(p, v, ca, cb, 0u, ent, cap, base, lt, irregular);
-    }
-    return base;
+    for (int j = 0; j < 8; j++) v[j] = 0.0f;
+    if (lane < n4) { const float4 t = ldg_stream4(b4 + lane); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    if (lane + 32u < n4) { const float4 t = ldg_stream4(b4 + lane + 32u); v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w; }
+}
+// ... and its entries (column * DP) are appended to ent[] from position `base`
+__device__ __noinline__ unsigned tc_row_emit(const FwdParams &p, const float (&v)[8], unsigned short *__restrict__ ent, unsigned cap, unsigned base, unsigned lane,
+                                             bool &irregular)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    if (!chunk_irregular<4>(v)) return emit_units_s(unit_mask<4>(v), lane, lane + 32u, 0u, p.DP, ent, cap, base, lt);
+    return emit_general_s(p, v, lane, lane + 32u, 0u, ent, cap, base, lt, irregular);
+}
+__device__ __forceinline__ unsigned ldg_na_u16(const void *ptr)
+{
+    unsigned short r;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(ptr));
+    return (unsigned)r;
 }
 
-// acc[j] += table codes of dims 16q.. over the entries of mini-record row `row` (entries in the warp's scratch at shared
-// address ent_sa, row ends in rend[]); table in global memory (L2).  Lanes without a row gather the all-zero row.
-__device__ __forceinline__ void tc_embed_glob(unsigned ent_sa, const unsigned short *rend, unsigned zaddr, const unsigned char *__restrict__ tabq, int row,
-                                              int acc[16], const int sel[4])
+// (a0, a1) += table codes of this lane's dims 2*lane, 2*lane+1 over entries [beg, end) of the warp's entry list (byte offsets
+// column * DP, DP = 64); table rows in global memory (L2-resident), one coalesced 64-byte row read per entry and warp.
+// Two rows at once (entries [0, na) and [na, nb)) so that their L2 round trips overlap.
+__device__ __forceinline__ void tc_gather2(unsigned ent_sa, unsigned na, unsigned nb, const unsigned char *__restrict__ tab, unsigned lane, int &a0, int &a1,
+                                           int &b0, int &b1)
 {
-#pragma unroll
-    for (int j = 0; j < 16; j++) acc[j] = 0;
-    unsigned beg = 0, len = 0;
-    if (row >= 0) {
-        beg = row ? rend[row - 1] : 0u;
-        len = rend[row] - beg;
-    }
-    const unsigned maxlen = __reduce_max_sync(0xffffffffu, len);
-    unsigned ea = ent_sa + 2u * beg;
-#pragma unroll 1
-    for (unsigned k0 = 0; k0 < maxlen; k0 += 4) {
-        uint4 t[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            unsigned short off;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(off) : "r"((k0 + i < len) ? ea + 2u * i : zaddr));
-            t[i] = __ldg(reinterpret_cast<const uint4 *>(tabq + off));
-        }
-        ea += 8u;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            acc[0] = __dp4a((int)t[i].x, sel[0], acc[0]);   acc[1] = __dp4a((int)t[i].x, sel[1], acc[1]);
-            acc[2] = __dp4a((int)t[i].x, sel[2], acc[2]);   acc[3] = __dp4a((int)t[i].x, sel[3], acc[3]);
-            acc[4] = __dp4a((int)t[i].y, sel[0], acc[4]);   acc[5] = __dp4a((int)t[i].y, sel[1], acc[5]);
-            acc[6] = __dp4a((int)t[i].y, sel[2], acc[6]);   acc[7] = __dp4a((int)t[i].y, sel[3], acc[7]);
-            acc[8] = __dp4a((int)t[i].z, sel[0], acc[8]);   acc[9] = __dp4a((int)t[i].z, sel[1], acc[9]);
-            acc[10] = __dp4a((int)t[i].z, sel[2], acc[10]); acc[11] = __dp4a((int)t[i].z, sel[3], acc[11]);
-            acc[12] = __dp4a((int)t[i].w, sel[0], acc[12]); acc[13] = __dp4a((int)t[i].w, sel[1], acc[13]);
-            acc[14] = __dp4a((int)t[i].w, sel[2], acc[14]); acc[15] = __dp4a((int)t[i].w, sel[3], acc[15]);
-        }
+    const unsigned char *t16 = tab + 2u * lane;
+    const unsigned lb_ = nb - na, n = max(na, lb_);
+#pragma unroll 4
+    for (unsigned e = 0; e < n; e++) {
+        unsigned short offa = 0, offb = 0;
+        if (e < na) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(offa) : "r"(ent_sa + 2u * e));
+        if (e < lb_) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(offb) : "r"(ent_sa + 2u * (na + e)));
+        unsigned wa = 0, wb = 0;
+        if (e < na) wa = ldg_na_u16(t16 + offa);
+        if (e < lb_) wb = ldg_na_u16(t16 + offb);
+        a0 += (int)(signed char)(wa & 0xFFu);
+        a1 += (int)(signed char)(wa >> 8);
+        b0 += (int)(signed char)(wb & 0xFFu);
+        b1 += (int)(signed char)(wb >> 8);
     }
 }
 
 // Packed scorer of one row held by this lane: y[w] = four dims of the row sum (bytes, weight format), query constants from
 // the warp's scratch (uniform addresses).  Returns 4 * score (+ 3 per dim) and the saturation flag; see swar_score.
-template <int KA>
-__device__ __forceinline__ int tc_score_row(const unsigned (&a)[16], unsigned sq_sa, unsigned (&y)[TC_DW], unsigned &flag)
+__device__ __forceinline__ int tc_score_row(unsigned sq_sa, const unsigned (&y)[TC_DW], unsigned &flag)
 {
     int D = 0;
     unsigned cs = 0, f = 0;
@@ -182,11 +183,7 @@ __device__ __forceinline__ int tc_score_row(const unsigned (&a)[16], unsigned sq
         unsigned Uw, Tw, U1, Us4;
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(Uw), "=r"(Tw), "=r"(U1), "=r"(Us4) : "r"(sq_sa + 16u * w));
         const unsigned U0 = Uw & SW_1, U0s = U0 << 1;
-        unsigned yy;
-        if (KA == 0) yy = a[w];
-        else if (KA > 0) yy = (a[w] << 1) & 0xFEFEFEFEu;
-        else yy = swar_half0(a[w]);
-        y[w] = yy;
+        const unsigned yy = y[w];
         unsigned fill;
         asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(fill) : "r"(yy));
         f |= ((yy ^ fill) + (fill & SW_1)) + Tw;                          // bit 7 of a byte: |y| >= tau(|u|)
@@ -206,6 +203,30 @@ __device__ __forceinline__ unsigned tc_pack4(unsigned b0, unsigned b1, unsigned 
     return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
 }
 __device__ __forceinline__ unsigned tc_ibits(unsigned fbits) { return __float_as_uint(__uint_as_float(fbits) + 12582912.0f); }      // low byte = the integer
+
+// z_i = sum_j fl(W_ij u_j), sequential fp32 without contraction (layer_cuda.cu:69-82); few rows per story need it
+__device__ __noinline__ float tc_exact_z(const float *__restrict__ wrow, const float *ufl, unsigned d4)
+{
+    const float4 *wr = reinterpret_cast<const float4 *>(wrow);
+    float z = 0.0f;
+#pragma unroll 4
+    for (unsigned j4 = 0; j4 < d4; j4++) {
+        const float4 ww = __ldg(wr + j4);
+        const float4 uu = *reinterpret_cast<const float4 *>(ufl + 4 * j4);
+        z = __fadd_rn(z, __fmul_rn(ww.x, uu.x));
+        z = __fadd_rn(z, __fmul_rn(ww.y, uu.y));
+        z = __fadd_rn(z, __fmul_rn(ww.z, uu.z));
+        z = __fadd_rn(z, __fmul_rn(ww.w, uu.w));
+    }
+    return z;
+}
+// a row with a saturating product: the reference order, product by product (rare)
+__device__ __noinline__ int tc_exact_row(const unsigned *y, const signed char *ub8, int la, int fb)
+{
+    int sp = 0;
+    for (unsigned j = 0; j < 4u * TC_DW; j++) sp += qi_mul(sbyte(y[j >> 2], j & 3), (int)ub8[j], la, fb);
+    return sp;
+}
 
 template <bool DUMP>
 __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_constant__ TcParams tp)
@@ -227,7 +248,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
 
     if (threadIdx.x == 0) {
         mbar_init(cb + TCB_TAB, 1);
-        for (unsigned s = 0; s < TC_NSTAGE; s++) { mbar_init(cb + TCB_FULL + 8 * s, 1); mbar_init(cb + TCB_EMPTY + 8 * s, 2); }
+        for (unsigned s = 0; s < TC_NSTAGE; s++) { mbar_init(cb + TCB_FULL + 8 * s, 1); mbar_init(cb + TCB_EMPTY + 8 * s, 1 + TC_NVAL); }
         for (unsigned i = 0; i < TC_MAX_TEAMS; i++) mbar_init(cb + TCB_DFULL + 8 * i, 1 + TC_NVAL);
         mbar_init(cb + TCB_DFREE, 4);
         for (unsigned i = 0; i < TC_NG; i++) mbar_init(cb + TCB_GBAR + 8 * i, 1);
@@ -235,6 +256,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
         tma_prefetch_desc(&tp.tmX);
         tma_prefetch_desc(&tp.tmT);
     }
+    if (threadIdx.x < 128) cbg[TCB_TAU + threadIdx.x] = p.img[p.offTAU + threadIdx.x];     // saturation thresholds tau[|u|]
     if (warp == TC_W_MMA) tmem_alloc(cb + TCB_TMEM, 512);
     tc_fence_before();
     __syncthreads();
@@ -248,6 +270,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
             for (unsigned k = 0; k < KCH; k++) tma_load_2d(tabs + k * TC_TABCH_BYTES, &tp.tmT, (int)(32 * k), 0, cb + TCB_TAB);
             unsigned it = 0;
             unsigned team_tiles[TC_MAX_TEAMS] = {0u, 0u, 0u, 0u};
+            TCK_DECL
             for (unsigned gl = 0;; gl++) {
                 const unsigned g = atomicAdd(p.counter, 1u);
                 TCT(0, 0x100u + gl); TCT(1, g);
@@ -257,6 +280,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
                         gd->n_tiles = 0;
                         mbar_arrive(cb + TCB_GBAR + 8 * ((gl + i) % TC_NG));
                     }
+                    TCK(1); TCK_FLUSH;
                     break;
                 }
                 TcGroup *gd = &gdesc[gl % TC_NG];
@@ -280,7 +304,9 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
                     for (unsigned k = 0; k < KCH; k++, it++) {
                         const unsigned s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
                         TCT(2, it);
+                        TCK(1);
                         mbar_wait(cb + TCB_EMPTY + 8 * s, ph ^ 1u);
+                        TCK(0);
                         TCT(3, it);
                         mbar_expect_tx(cb + TCB_FULL + 8 * s, TC_STAGE_BYTES);
                         for (unsigned j = 0; j < 4; j++) {
@@ -298,19 +324,25 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
             mbar_wait(cb + TCB_TAB, 0);
             TCT(0, 2u);
             unsigned it = 0, tcnt = 0;
+            TCK_DECL
             for (unsigned gl = 0;; gl++) {
                 mbar_wait(cb + TCB_GBAR + 8 * (gl % TC_NG), (gl / TC_NG) & 1u);
                 const unsigned n_tiles = gdesc[gl % TC_NG].n_tiles;
-                if (n_tiles == 0) break;
+                TCK(3);
+                if (n_tiles == 0) { TCK_FLUSH; break; }
                 for (unsigned t = 0; t < n_tiles; t++, tcnt++) {
                     TCT(0, 0x1000u + tcnt);
+                    TCK(2);
                     mbar_wait(cb + TCB_DFREE, (tcnt & 1u) ^ 1u);
+                    TCK(0);
                     TCT(0, 0x2000u + tcnt);
                     tc_fence_after();
                     for (unsigned k = 0; k < KCH; k++, it++) {
                         const unsigned s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
                         TCT(1, it);
+                        TCK(2);
                         mbar_wait(cb + TCB_FULL + 8 * s, ph);
+                        TCK(1);
                         TCT(2, it);
                         tc_fence_after();
 #pragma unroll
@@ -327,21 +359,22 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
         // ================= validators =================
         const unsigned v = warp - TC_W_VAL0;
         unsigned it = 0;
+        TCK_DECL
         for (unsigned gl = 0;; gl++) {
             mbar_wait(cb + TCB_GBAR + 8 * (gl % TC_NG), (gl / TC_NG) & 1u);
             const TcGroup *gd = &gdesc[gl % TC_NG];
             const unsigned n_tiles = gd->n_tiles;
-            if (n_tiles == 0) break;
+            TCK(3);
+            if (n_tiles == 0) { TCK_FLUSH; break; }
             for (unsigned t = 0; t < n_tiles; t++) {
                 for (unsigned k = 0; k < KCH; k++, it++) {
-                    // this warp owns ring stage v: it sees every phase of full[v] and is one of the two arrivals that release it,
-                    // so the barrier can never run two phases ahead of its wait
                     const unsigned s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
-                    if (s != v) continue;
                     TCT(0, it);
+                    TCK(1);
                     mbar_wait(cb + TCB_FULL + 8 * s, ph);
+                    TCK(0);
                     TCT(1, it);
-                    tc_validate_stage(p, gbase + (ring - sbase) + s * TC_STAGE_BYTES, t, k, gd, badf + (gl % TC_NG) * 4, lane);
+                    tc_validate_stage(p, gbase + (ring - sbase) + s * TC_STAGE_BYTES, t, k, gd, badf + (gl % TC_NG) * 4, lane, v);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(cb + TCB_EMPTY + 8 * s);
                 }
@@ -367,31 +400,31 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
         __syncwarp();
         const unsigned tq = tmem + ((32u * q) << 16);
         const unsigned tpk = tq + TC_NT + team * (2u * TC_PK_COLS);
-        constexpr int LPR = 4, G = 8;
-        const unsigned g8 = lane / LPR, ql = lane % LPR;
-        int sel[4];
-        asm volatile("mov.u32 %0, 0x00000001;" : "=r"(sel[0]));
-        asm volatile("mov.u32 %0, 0x00000100;" : "=r"(sel[1]));
-        asm volatile("mov.u32 %0, 0x00010000;" : "=r"(sel[2]));
-        asm volatile("mov.u32 %0, 0x01000000;" : "=r"(sel[3]));
-        const unsigned char *tau = p.img + p.offTAU;
+        const unsigned char *tau = cbg + TCB_TAU;
         const unsigned row_floats = V;
 
+        TCK_DECL
 #pragma unroll 1
         for (unsigned gl = team;; gl += tp.n_teams) {
             TCT(0, 0x100u + gl);
+            TCK(3);
             mbar_wait(cb + TCB_GBAR + 8 * (gl % TC_NG), (gl / TC_NG) & 1u);
+            TCK(0);
             const TcGroup *gd = &gdesc[gl % TC_NG];
             const unsigned n_tiles = gd->n_tiles;
             TCT(0, 0x200u + gl); TCT(1, n_tiles);
-            if (n_tiles == 0) break;
+            if (n_tiles == 0) { TCK_FLUSH; break; }
             const unsigned w = gd->story[q], S = gd->S[q], tile_base = gd->tile_base;
             const unsigned long long soff = gd->soff[q];
             bool decline = false;
+            if (w != 0xFFFFFFFFu && lane < (V * 4u + 127u) / 128u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p.dq + (size_t)(p.story0 + w) * V) + 128u * lane));
             // ---- row sums of my story: accumulator tile -> bytes -> my packed slot ----
             for (unsigned t = 0; t < n_tiles; t++) {
                 TCT(2, 0x100u + tile_base + t);
+                TCK(2);
                 mbar_wait(cb + TCB_DFULL + 8 * team, (tile_base + t) & 1u);
+                TCK(1);
                 TCT(2, 0x200u + tile_base + t);
                 tc_fence_after();
                 const bool rvalid = (32u * t + lane) < S;
@@ -408,20 +441,21 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
                 }
                 decline |= __any_sync(0xffffffffu, wide && rvalid);
                 for (unsigned h = 0; h < p.H; h++) {
-                    unsigned pk[16];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        unsigned v[16];
-                        tmem_ld16(tq + TC_HCOLS * h + 16u * c, v);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 4; i++) pk[4 * c + i] = tc_pack4(tc_ibits(v[4 * i]), tc_ibits(v[4 * i + 1]), tc_ibits(v[4 * i + 2]), tc_ibits(v[4 * i + 3]));
-                    }
+                    unsigned pk[13];
                     {
-                        unsigned v[4];
-                        tmem_ld4(tq + TC_HCOLS * h + 48u, v);
+                        unsigned v0[16], v1[16], v2[16], v3[4];
+                        tmem_ld16(tq + TC_HCOLS * h, v0);
+                        tmem_ld16(tq + TC_HCOLS * h + 16u, v1);
+                        tmem_ld16(tq + TC_HCOLS * h + 32u, v2);
+                        tmem_ld4(tq + TC_HCOLS * h + 48u, v3);
                         tmem_wait_ld();
-                        pk[12] = tc_pack4(tc_ibits(v[0]), tc_ibits(v[1]), tc_ibits(v[2]), tc_ibits(v[3]));
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            pk[i] = tc_pack4(tc_ibits(v0[4 * i]), tc_ibits(v0[4 * i + 1]), tc_ibits(v0[4 * i + 2]), tc_ibits(v0[4 * i + 3]));
+                            pk[4 + i] = tc_pack4(tc_ibits(v1[4 * i]), tc_ibits(v1[4 * i + 1]), tc_ibits(v1[4 * i + 2]), tc_ibits(v1[4 * i + 3]));
+                            pk[8 + i] = tc_pack4(tc_ibits(v2[4 * i]), tc_ibits(v2[4 * i + 1]), tc_ibits(v2[4 * i + 2]), tc_ibits(v2[4 * i + 3]));
+                        }
+                        pk[12] = tc_pack4(tc_ibits(v3[0]), tc_ibits(v3[1]), tc_ibits(v3[2]), tc_ibits(v3[3]));
                     }
                     const unsigned dst = tpk + TC_PK_COLS * t + TC_DW * h;
                     {
@@ -434,14 +468,18 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(cb + TCB_DFREE);
+                TCK(2);
                 TCT(2, 0x300u + tile_base + t);
             }
-            if (w == 0xFFFFFFFFu) continue;                                   // empty quadrant of the last group
+            // The four warps of a team run their stories in step (a named barrier per phase): they then fetch the same
+            // instruction lines at the same time, and the 32 KB instruction cache holds the four teams' positions.
+            const bool empty = (w == 0xFFFFFFFFu);                            // empty quadrant of the last group
             decline |= (badf[(gl % TC_NG) * 4 + q] != 0) || (S == 0u);
+            bool dead = empty;
             const unsigned story = p.story0 + w;
             const unsigned nrs = S > 32u ? 2u : 1u;
             unsigned ans_idx = ANS_NONE;
-            if (p.da) {
+            if (p.da && !dead) {
                 const float *arow = p.da + (size_t)story * V;
                 for (unsigned c0 = 0; c0 < V; c0 += 32) {
                     const unsigned c = c0 + lane;
@@ -450,39 +488,38 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
                     if (bb) ans_idx = c0 + 31 - __clz(bb);
                 }
             }
-            int acc[16];
             // ---- question embedding u0 = Q_w0(sum)                          MemN2N.c:826, layer_cuda.cu:49 ----
-            if (!decline) {
+            // From here on lane l owns dims 2l, 2l+1 of every d-vector (u, o, g): gathers read one coalesced 64-byte table row
+            // per entry, sums and updates stay in the lane's registers.
+            const unsigned c0 = 2u * lane;
+            int u0c = 0, u1c = 0;                                             // controller state, codes with fu fractional bits
+            if (!decline && !dead) {
                 bool irregular = false;
-                const unsigned n = tc_scan_row_g(p, p.dq + (size_t)story * row_floats, ent, TC_ENT_CAP, 0u, lane, irregular);
-                if (lane == 0) rend[0] = (unsigned short)min(n, 0xFFFFu);
+                float qv[8];
+                tc_row_load(p, p.dq + (size_t)story * row_floats, lane, qv);
+                const unsigned n = tc_row_emit(p, qv, ent, TC_ENT_CAP, 0u, lane, irregular);
                 decline = irregular || n > TC_ENT_CAP;
                 __syncwarp();
-            }
-            if (decline) {
-                if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = w;
-                continue;
-            }
-            TCT(3, 1u);
-            tc_embed_glob(ent_sa, rend, zaddr, p.img + p.offB + 16u * ql, (g8 == 0) ? 0 : -1, acc, sel);
-            if (g8 == 0) {
-                unsigned packed[4];
-#pragma unroll
-                for (int w4 = 0; w4 < 4; w4++) {
-                    unsigned v = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; b++) v |= ((unsigned)(qi_clamp(acc[4 * w4 + b], p.lw[0]) & 0xFF)) << (8 * b);
-                    packed[w4] = v;
+                if (!decline) {
+                    int x0 = 0, x1 = 0;
+                    tc_gather2(ent_sa, n, n, p.img + p.offB, lane, u0c, u1c, x0, x1);
+                    u0c = qi_clamp(u0c, p.lw[0]); u1c = qi_clamp(u1c, p.lw[0]);
                 }
-                *reinterpret_cast<uint4 *>(uvec + 16 * ql) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
-            __syncwarp();
+            if (decline && !dead) {
+                if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = w;
+                dead = true;
+            }
             int fu = p.fw[0];
-            if (DUMP && p.dbg.dev_u0)
-                for (unsigned j = lane; j < d; j += 32) p.dbg.dev_u0[(size_t)story * d + j] = (float)uvec[j] / (float)(1 << fu);
+            if (DUMP && p.dbg.dev_u0 && !dead) {
+                if (c0 < d) p.dbg.dev_u0[(size_t)story * d + c0] = (float)u0c / (float)(1 << fu);
+                if (c0 + 1 < d) p.dbg.dev_u0[(size_t)story * d + c0 + 1] = (float)u1c / (float)(1 << fu);
+            }
 
 #pragma unroll 1
-            for (unsigned h = 0; h < p.H && !decline; h++) {
+            for (unsigned h = 0; h < p.H; h++) {
+                asm volatile("bar.sync %0, 128;" ::"r"(1u + team) : "memory");
+                if (!dead) do {
                 const int fw = p.fw[h], lw = p.lw[h];
                 const int fa = p.fa[h], la = p.la[h];
                 const int ff = p.ff[h], lf = p.lf[h];
@@ -490,10 +527,10 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
                 const int ka = fa - fw;
                 TCT(3, 0x10u + h);
                 // Q_bin(u) and the saturation thresholds as bytes, then the per-word query constants  MemN2N.c:847,873
-                for (unsigned j = lane; j < 64; j += 32) {
-                    const int u = (j < d) ? qi_requant((int)uvec[j], fu, lb, fb) : 0;
-                    ub8[j] = (signed char)u;
-                    tw8[j] = __ldg(tau + abs(u));
+                {
+                    const int b0 = (c0 < d) ? qi_requant(u0c, fu, lb, fb) : 0, b1 = (c0 + 1 < d) ? qi_requant(u1c, fu, lb, fb) : 0;
+                    *reinterpret_cast<unsigned short *>(ub8 + c0) = (unsigned short)((b0 & 0xFF) | ((b1 & 0xFF) << 8));
+                    *reinterpret_cast<unsigned short *>(tw8 + c0) = (unsigned short)((unsigned)tau[abs(b0)] | ((unsigned)tau[abs(b1)] << 8));
                 }
                 __syncwarp();
                 if (lane < TC_DW) {
@@ -509,22 +546,21 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
                     tmem_ld16(tpk + TC_PK_COLS * rs + TC_DW * h, a);
                     tmem_wait_ld();
                     unsigned y[TC_DW], flag;
-                    int part;
-                    if (ka == 0) part = tc_score_row<0>(a, sq_sa, y, flag);
-                    else if (ka > 0) part = tc_score_row<1>(a, sq_sa, y, flag);
-                    else part = tc_score_row<-1>(a, sq_sa, y, flag);
-                    int tot = part >> 2;                                       // exact: a multiple of 4
-                    if (flag != 0u && (32u * rs + lane) < S) {
-                        // some product of this row saturates: the reference order, product by product
-                        int sp = 0;
-                        for (unsigned j = 0; j < 4u * TC_DW; j++) {
-                            const unsigned yw = (j < 4) ? y[0] : (j < 8) ? y[1] : (j < 12) ? y[2] : (j < 16) ? y[3] : (j < 20) ? y[4] : (j < 24) ? y[5] : (j < 28) ? y[6]
-                                                : (j < 32) ? y[7] : (j < 36) ? y[8] : (j < 40) ? y[9] : (j < 44) ? y[10] : (j < 48) ? y[11] : y[12];
-                            sp += qi_mul(sbyte(yw, j & 3), (int)ub8[j], la, fb);
-                        }
-                        tot = sp;
+                    // Q_att of the row sums: same grid, one more fractional bit (2a, exact: 2B <= 127), or one less (trunc0(a / 2))
+                    if (ka == 0) {
+#pragma unroll
+                        for (unsigned w_ = 0; w_ < TC_DW; w_++) y[w_] = a[w_];
+                    } else if (ka > 0) {
+#pragma unroll
+                        for (unsigned w_ = 0; w_ < TC_DW; w_++) y[w_] = (a[w_] << 1) & 0xFEFEFEFEu;
+                    } else {
+#pragma unroll
+                        for (unsigned w_ = 0; w_ < TC_DW; w_++) y[w_] = swar_half0(a[w_]);
                     }
-                    scode[rs] = qi_clamp(tot, la);
+                    const int part = tc_score_row(sq_sa, y, flag);
+                    int tot = part >> 2;                                       // exact: a multiple of 4
+                    if (flag != 0u && (32u * rs + lane) < S) tot = tc_exact_row(y, ub8, la, fb);
+                    if (rs == 0) scode[0] = qi_clamp(tot, la); else scode[1] = qi_clamp(tot, la);
                 }
                 // ---- attention normalisation (layer_cuda.cu:1895-1916, 1969-2060) ----
                 float sv[2], ev[2];
@@ -565,6 +601,7 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
                 }
                 if (exact_total) {
                     double total = 0.0;
+#pragma unroll 1
                     for (unsigned r = 0; r < S; r++) total += (double)__shfl_sync(0xffffffffu, (r < 32u) ? ev[0] : ev[1], (int)(r & 31u));
 #pragma unroll
                     for (int rs = 0; rs < 2; rs++)
@@ -586,242 +623,172 @@ __global__ void __launch_bounds__(TC_WARPS * 32, 1) k_story_tc(const __grid_cons
                 if (nnz > TC_NNZ_CAP) { decline = true; break; }
                 __syncwarp();
                 // ---- weighted read over the selected slots (layer_cuda.cu:547-579): their C_h rows from the dense rows ----
+                int o0 = 0, o1 = 0;
                 {
-                    unsigned base = 0;
                     bool irregular = false;
-                    for (unsigned k = 0; k < nnz; k++) {
-                        base = tc_scan_row_g(p, p.dm + (soff + selr[k]) * (size_t)row_floats, ent, TC_ENT_CAP, base, lane, irregular);
-                        if (lane == 0) rend[k] = (unsigned short)min(base, 0xFFFFu);
-                    }
-                    if (irregular || base > TC_ENT_CAP) { decline = true; break; }
-                    __syncwarp();
-                }
-                int oacc[16];
-#pragma unroll
-                for (int j = 0; j < 16; j++) oacc[j] = 0;
-                const unsigned char *ctab = p.img + p.offC[h] + 16u * ql;
+                    const unsigned char *ctab = p.img + p.offC[h];
 #pragma unroll 1
-                for (unsigned k0 = 0; k0 < nnz; k0 += G) {
-                    const unsigned k = k0 + g8;
-                    const int pc = (k < nnz) ? (int)pq[k] : 0;
-                    tc_embed_glob(ent_sa, rend, zaddr, ctab, (k < nnz) ? (int)k : -1, acc, sel);
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int c_f = qi_requant(qi_clamp(acc[j], lw), fw, lf, ff);
-                        oacc[j] += qi_mul(pc, c_f, lf, ff);
-                    }
-                }
-#pragma unroll
-                for (int o = LPR; o < 32; o <<= 1)
-#pragma unroll
-                    for (int j = 0; j < 16; j++) oacc[j] += __shfl_xor_sync(0xffffffffu, oacc[j], o);
-                if (g8 == 0) {
-                    unsigned packed[4];
-#pragma unroll
-                    for (int w4 = 0; w4 < 4; w4++) {
-                        unsigned v = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; b++) v |= ((unsigned)(qi_clamp(oacc[4 * w4 + b], lf) & 0xFF)) << (8 * b);
-                        packed[w4] = v;
-                    }
-                    *reinterpret_cast<uint4 *>(ovec + 16 * ql) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                }
-                __syncwarp();
-                if (DUMP && p.dbg.dev_o)
-                    for (unsigned j = lane; j < d; j += 32) p.dbg.dev_o[((size_t)h * p.n_total + story) * d + j] = (float)ovec[j] / (float)(1 << ff);
-
-                // ---- linear map (MemN2N.c:873, layer_cuda.cu:49-68) and update (MemN2N.c:889, layer_cuda.cu:1535) ----
-                if (p.lin_map) {
-                    int gacc[16];
-#pragma unroll
-                    for (int k = 0; k < 16; k++) gacc[k] = 0;
-                    const signed char *lut = p.lut + p.offL[h] + 16u * ql;
-#pragma unroll 1
-                    for (unsigned jb = 0; jb < d; jb += 8 * G) {
-                        uint4 t[8];
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const unsigned j = jb + (unsigned)i * G + g8;
-                            t[i] = make_uint4(0u, 0u, 0u, 0u);
-                            if (j < d) t[i] = __ldg(reinterpret_cast<const uint4 *>(lut + (size_t)(j * 255u + (unsigned)((int)ub8[j] + 127)) * DP));
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            gacc[0] = __dp4a((int)t[i].x, sel[0], gacc[0]);   gacc[1] = __dp4a((int)t[i].x, sel[1], gacc[1]);
-                            gacc[2] = __dp4a((int)t[i].x, sel[2], gacc[2]);   gacc[3] = __dp4a((int)t[i].x, sel[3], gacc[3]);
-                            gacc[4] = __dp4a((int)t[i].y, sel[0], gacc[4]);   gacc[5] = __dp4a((int)t[i].y, sel[1], gacc[5]);
-                            gacc[6] = __dp4a((int)t[i].y, sel[2], gacc[6]);   gacc[7] = __dp4a((int)t[i].y, sel[3], gacc[7]);
-                            gacc[8] = __dp4a((int)t[i].z, sel[0], gacc[8]);   gacc[9] = __dp4a((int)t[i].z, sel[1], gacc[9]);
-                            gacc[10] = __dp4a((int)t[i].z, sel[2], gacc[10]); gacc[11] = __dp4a((int)t[i].z, sel[3], gacc[11]);
-                            gacc[12] = __dp4a((int)t[i].w, sel[0], gacc[12]); gacc[13] = __dp4a((int)t[i].w, sel[1], gacc[13]);
-                            gacc[14] = __dp4a((int)t[i].w, sel[2], gacc[14]); gacc[15] = __dp4a((int)t[i].w, sel[3], gacc[15]);
-                        }
-                    }
-#pragma unroll
-                    for (int o = LPR; o < 32; o <<= 1)
-#pragma unroll
-                        for (int k = 0; k < 16; k++) gacc[k] += __shfl_xor_sync(0xffffffffu, gacc[k], o);
-                    if (g8 == 0) {
-                        const uint4 o4 = *reinterpret_cast<const uint4 *>(ovec + 16 * ql);
-                        const unsigned ow[4] = {o4.x, o4.y, o4.z, o4.w};
-                        unsigned packed[4];
-#pragma unroll
-                        for (int w4 = 0; w4 < 4; w4++) {
-                            unsigned v = 0;
-#pragma unroll
-                            for (int b = 0; b < 4; b++) {
-                                const int g_w = qi_clamp(gacc[4 * w4 + b], lw);
-                                if (DUMP && p.dbg.dev_g && 16u * ql + 4 * w4 + b < d)
-                                    p.dbg.dev_g[((size_t)h * p.n_total + story) * d + 16u * ql + 4 * w4 + b] = (float)g_w / (float)(1 << fw);
-                                const int a_f = qi_requant(g_w, fw, lf, ff);
-                                v |= ((unsigned)(qi_clamp(a_f + sbyte(ow[w4], b), lf) & 0xFF)) << (8 * b);
-                            }
-                            packed[w4] = v;
-                        }
-                        *reinterpret_cast<uint4 *>(uvec + 16 * ql) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    }
-                } else {
-                    for (unsigned i = lane; i < 64; i += 32) {
-                        const int g_w = (i < d) ? (int)uvec[i] : 0;
-                        const int a_f = qi_requant(g_w, fu, lf, ff);
-                        if (DUMP && p.dbg.dev_g && i < d) p.dbg.dev_g[((size_t)h * p.n_total + story) * d + i] = (float)g_w / (float)(1 << fu);
+                    for (unsigned k = 0; k < nnz; k += 2) {
+                        // two selected slots per step: their dense rows are loaded together, then their C_h rows gathered together
+                        const bool two = (k + 1 < nnz);
+                        float va[8], vb[8];
+                        tc_row_load(p, p.dm + (soff + selr[k]) * (size_t)row_floats, lane, va);
+                        tc_row_load(p, p.dm + (soff + selr[two ? k + 1 : k]) * (size_t)row_floats, lane, vb);
+                        const unsigned na = tc_row_emit(p, va, ent, TC_ENT_CAP, 0u, lane, irregular);
+                        const unsigned nb = two ? tc_row_emit(p, vb, ent, TC_ENT_CAP, na, lane, irregular) : na;
+                        if (irregular || nb > TC_ENT_CAP) { irregular = true; break; }
                         __syncwarp();
-                        uvec[i] = (i < d) ? (signed char)qi_clamp(a_f + (int)ovec[i], lf) : (signed char)0;
+                        int a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+                        tc_gather2(ent_sa, na, nb, ctab, lane, a0, a1, b0, b1);
+                        const int pa = (int)pq[k], pb = two ? (int)pq[k + 1] : 0;
+                        o0 += qi_mul(pa, qi_requant(qi_clamp(a0, lw), fw, lf, ff), lf, ff) + qi_mul(pb, qi_requant(qi_clamp(b0, lw), fw, lf, ff), lf, ff);
+                        o1 += qi_mul(pa, qi_requant(qi_clamp(a1, lw), fw, lf, ff), lf, ff) + qi_mul(pb, qi_requant(qi_clamp(b1, lw), fw, lf, ff), lf, ff);
+                        __syncwarp();
                     }
+                    if (irregular) { decline = true; break; }
                 }
+                o0 = qi_clamp(o0, lf); o1 = qi_clamp(o1, lf);
+                if (DUMP && p.dbg.dev_o) {
+                    if (c0 < d) p.dbg.dev_o[((size_t)h * p.n_total + story) * d + c0] = (float)o0 / (float)(1 << ff);
+                    if (c0 + 1 < d) p.dbg.dev_o[((size_t)h * p.n_total + story) * d + c0 + 1] = (float)o1 / (float)(1 << ff);
+                }
+                // ---- linear map (MemN2N.c:873, layer_cuda.cu:49-68) and update (MemN2N.c:889, layer_cuda.cu:1535) ----
+                int g0, g1, gfrac;
+                if (p.lin_map) {
+                    // g[i] = Q_w(sum_j T[j][Q_bin(u[j])][i]): every product Q_w(Q_w(Hm[i][j]) * Q_bin(u[j])) is one byte of a table row
+                    g0 = 0; g1 = 0;
+                    const unsigned short *lut16 = reinterpret_cast<const unsigned short *>(p.lut + p.offL[h]) + lane;
+#pragma unroll 25
+                    for (unsigned j = 0; j < d; j++) {
+                        const unsigned row = j * 255u + (unsigned)((int)ub8[j] + 127);
+                        const unsigned w_ = ldg_na_u16(lut16 + (size_t)row * (DP / 2));
+                        g0 += (int)(signed char)(w_ & 0xFFu);
+                        g1 += (int)(signed char)(w_ >> 8);
+                    }
+                    g0 = qi_clamp(g0, lw); g1 = qi_clamp(g1, lw);
+                    gfrac = fw;
+                } else {
+                    g0 = u0c; g1 = u1c; gfrac = fu;
+                }
+                if (DUMP && p.dbg.dev_g) {
+                    if (c0 < d) p.dbg.dev_g[((size_t)h * p.n_total + story) * d + c0] = (float)g0 / (float)(1 << gfrac);
+                    if (c0 + 1 < d) p.dbg.dev_g[((size_t)h * p.n_total + story) * d + c0 + 1] = (float)g1 / (float)(1 << gfrac);
+                }
+                u0c = (c0 < d) ? qi_clamp(qi_requant(g0, gfrac, lf, ff) + o0, lf) : 0;
+                u1c = (c0 + 1 < d) ? qi_clamp(qi_requant(g1, gfrac, lf, ff) + o1, lf) : 0;
                 fu = ff;
+                if (DUMP && p.dbg.dev_u) {
+                    if (c0 < d) p.dbg.dev_u[((size_t)h * p.n_total + story) * d + c0] = (float)u0c / (float)(1 << fu);
+                    if (c0 + 1 < d) p.dbg.dev_u[((size_t)h * p.n_total + story) * d + c0 + 1] = (float)u1c / (float)(1 << fu);
+                }
                 __syncwarp();
-                if (DUMP && p.dbg.dev_u)
-                    for (unsigned j = lane; j < d; j += 32) p.dbg.dev_u[((size_t)h * p.n_total + story) * d + j] = (float)uvec[j] / (float)(1 << fu);
+                } while (0);
+                if (decline && !dead) {
+                    if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = w;
+                    dead = true;
+                }
             }
-            if (decline) {
-                if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = w;
-                continue;
-            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1u + team) : "memory");
+            if (dead) continue;
 
             TCT(3, 0x50u);
-            // ---- answer projection with the int8 prefilter (see k_story), logits in registers, W8 and W rows from L2 ----
-            for (unsigned j = lane; j < 64; j += 32) ufl[j] = (j < d) ? (float)uvec[j] / (float)(1 << fu) : 0.0f;
+            // ---- answer projection with the int8 prefilter (see k_story): W8 and the fp32 rows from L2 ----
+            // z_i = sum_j fl(W_ij u_j) in index order is needed exactly only for the rows that can hold the largest probability:
+            // the integer dot D_i = sum_j W8_ij n_j bounds z_i, every row within 1e-5 of the best logit has D_i >= D_max - T.
+            *reinterpret_cast<unsigned short *>(uvec + c0) = (unsigned short)((u0c & 0xFF) | ((u1c & 0xFF) << 8));
+            ufl[c0] = (float)u0c / (float)(1 << fu);
+            ufl[c0 + 1] = (float)u1c / (float)(1 << fu);
             __syncwarp();
             const unsigned d4 = (d + 3) / 4;
             const float *Wg = reinterpret_cast<const float *>(p.img + p.offW);
-            auto exact_z = [&](unsigned i) {
-                const float4 *wr = reinterpret_cast<const float4 *>(Wg + (size_t)i * p.WS);
-                float z = 0.0f;
+            const unsigned nw16 = (d + 15) / 16;
+            const unsigned char *W8g = p.img + p.offW8;
+            auto w8_dot = [&](unsigned i) {
+                const unsigned char *wrow = W8g + (size_t)min(i, V - 1) * p.W8S;
+                int D = 0;
 #pragma unroll 4
-                for (unsigned j4 = 0; j4 < d4; j4++) {
-                    const float4 ww = __ldg(wr + j4);
-                    const float4 uu = *reinterpret_cast<const float4 *>(ufl + 4 * j4);
-                    z = __fadd_rn(z, __fmul_rn(ww.x, uu.x));
-                    z = __fadd_rn(z, __fmul_rn(ww.y, uu.y));
-                    z = __fadd_rn(z, __fmul_rn(ww.z, uu.z));
-                    z = __fadd_rn(z, __fmul_rn(ww.w, uu.w));
+                for (unsigned w16 = 0; w16 < nw16; w16++) {
+                    const uint4 ww = __ldg(reinterpret_cast<const uint4 *>(wrow + 16u * w16));
+                    const uint4 uu = *reinterpret_cast<const uint4 *>(uvec + 16 * w16);
+                    D = __dp4a((int)ww.x, (int)uu.x, D);
+                    D = __dp4a((int)ww.y, (int)uu.y, D);
+                    D = __dp4a((int)ww.z, (int)uu.z, D);
+                    D = __dp4a((int)ww.w, (int)uu.w, D);
                 }
-                return z;
+                return D;
             };
-            float zr[8];                      // logits / exponentials of rows i = 32 k + lane
-#pragma unroll
-            for (int k = 0; k < 8; k++) zr[k] = -INFINITY;
-            float zmax = -INFINITY;
             unsigned n_cand = 0, cand_idx = 0;
             bool need_full = !p.w8_ok || p.want_h;
             if (!need_full) {
-                int n1 = 0;
-                for (unsigned j = lane; j < 64; j += 32) n1 += abs((int)uvec[j]);
+                int n1 = abs(u0c) + abs(u1c);
                 n1 = __reduce_add_sync(0xffffffffu, n1);
                 const int T = n1 + (n1 >> 6) + p.ans_margin + 2;
-                const unsigned nw16 = (d + 15) / 16;
-                const unsigned char *W8g = p.img + p.offW8;
-                int Dv[8];
                 int Dmax = INT_MIN;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const unsigned i = 32u * k + lane;
-                    int D = 0;
-                    if (32u * k < V) {
-                        const unsigned char *wrow = W8g + (size_t)min(i, V - 1) * p.W8S;
-#pragma unroll 4
-                        for (unsigned w16 = 0; w16 < nw16; w16++) {
-                            const uint4 ww = __ldg(reinterpret_cast<const uint4 *>(wrow + 16u * w16));
-                            const uint4 uu = *reinterpret_cast<const uint4 *>(uvec + 16 * w16);
-                            D = __dp4a((int)ww.x, (int)uu.x, D);
-                            D = __dp4a((int)ww.y, (int)uu.y, D);
-                            D = __dp4a((int)ww.z, (int)uu.z, D);
-                            D = __dp4a((int)ww.w, (int)uu.w, D);
-                        }
-                    }
-                    Dv[k] = (i < V) ? D : INT_MIN;
-                    Dmax = max(Dmax, Dv[k]);
-                }
+#pragma unroll 2
+                for (unsigned i = lane; i < V; i += 32) Dmax = max(Dmax, w8_dot(i));
                 Dmax = __reduce_max_sync(0xffffffffu, Dmax);
                 const int thr = Dmax - T;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const unsigned i = 32u * k + lane;
-                    if (i < V) {
-                        const bool cnd = Dv[k] >= thr;
-                        if (cnd) zr[k] = exact_z(i);
-                        zmax = fmaxf(zmax, zr[k]);
-                        if (DUMP && p.dbg.dev_cand) p.dbg.dev_cand[(size_t)story * V + i] = cnd ? 1 : 0;
-                        if (DUMP && p.dbg.dev_z) p.dbg.dev_z[(size_t)story * V + i] = zr[k];
+                // second pass: the candidates' exact logits; per lane the two largest are enough to see a near-tie
+                float z1 = -INFINITY, z2 = -INFINITY;
+                unsigned i1 = 0;
+#pragma unroll 1
+                for (unsigned i = lane; i < V; i += 32) {
+                    const bool cnd = w8_dot(i) >= thr;
+                    float z = -INFINITY;
+                    if (cnd) z = tc_exact_z(Wg + (size_t)i * p.WS, ufl, d4);
+                    if (DUMP && p.dbg.dev_cand) p.dbg.dev_cand[(size_t)story * V + i] = cnd ? 1 : 0;
+                    if (DUMP && p.dbg.dev_z) p.dbg.dev_z[(size_t)story * V + i] = z;
+                    if (cnd) {
+                        if (!(z1 > z)) { z2 = z1; z1 = z; i1 = i; }            // ties keep the larger index in (z1, i1)
+                        else if (z > z2) z2 = z;
                     }
                 }
+                float zmax = z1;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const unsigned i = 32u * k + lane;
-                    const bool cand = (i < V) && (__expf(zr[k] - zmax) >= 0.99999905f);
-                    const unsigned b = __ballot_sync(0xffffffffu, cand);
-                    if (b) { n_cand += __popc(b); cand_idx = 32u * k + 31 - __clz(b); }
-                }
-                need_full = n_cand > 1;                          // near-tie: the double total decides, every row exactly
-            }
-            if (need_full) {
-                zmax = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const unsigned i = 32u * k + lane;
-                    if (i < V) {
-                        zr[k] = exact_z(i);
-                        zmax = fmaxf(zmax, zr[k]);
-                        if (DUMP && p.dbg.dev_cand) p.dbg.dev_cand[(size_t)story * V + i] = 2;
-                        if (DUMP && p.dbg.dev_z) p.dbg.dev_z[(size_t)story * V + i] = zr[k];
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-                n_cand = 0; cand_idx = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const unsigned i = 32u * k + lane;
-                    bool cand = false;
-                    if (i < V) {
-                        zr[k] = __expf(zr[k] - zmax);
-                        cand = (zr[k] >= 0.99999905f);
-                    } else zr[k] = 0.0f;
-                    const unsigned b = __ballot_sync(0xffffffffu, cand);
-                    if (b) { n_cand += __popc(b); cand_idx = 32u * k + 31 - __clz(b); }
-                }
+                const bool c1 = __expf(z1 - zmax) >= 0.99999905f, c2 = __expf(z2 - zmax) >= 0.99999905f;
+                const unsigned b1 = __ballot_sync(0xffffffffu, c1), b2 = __ballot_sync(0xffffffffu, c2);
+                n_cand = __popc(b1) + __popc(b2);
+                cand_idx = __shfl_sync(0xffffffffu, i1, b1 ? (31 - __clz(b1)) : 0);
+                need_full = n_cand != 1;                         // near-tie: the double total decides, every row exactly
             }
             unsigned pred_i = cand_idx;
             float h_true_v = 0.0f;
-            if (need_full && ((n_cand > 1) || p.want_h)) {
-                double total = 0.0;
+            if (need_full) {
+                // every row exactly; h_i = fl(e_i / total) with the double total in index order (layer_cuda.cu:1969-2060),
+                // argmax with the last index among equals (layer_cuda.cu:1918-1939)
+                float er[8];
+                float zmax = -INFINITY;
+#pragma unroll 1
+                for (unsigned k = 0; k < 8; k++) {
+                    const unsigned i = 32u * k + lane;
+                    float z = -INFINITY;
+                    if (i < V) {
+                        z = tc_exact_z(Wg + (size_t)i * p.WS, ufl, d4);
+                        if (DUMP && p.dbg.dev_cand) p.dbg.dev_cand[(size_t)story * V + i] = 2;
+                        if (DUMP && p.dbg.dev_z) p.dbg.dev_z[(size_t)story * V + i] = z;
+                    }
+                    er[k] = z;
+                    zmax = fmaxf(zmax, z);
+                }
 #pragma unroll
-                for (int k = 0; k < 8; k++)
-                    if (32u * k < V)
-                        for (unsigned l = 0; l < 32; l++) {
-                            const float e = __shfl_sync(0xffffffffu, zr[k], (int)l);
-                            if (32u * k + l < V) total += (double)e;
-                        }
+                for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+                double total = 0.0;
+#pragma unroll 1
+                for (unsigned k = 0; k < 8; k++) {
+                    const unsigned i = 32u * k + lane;
+                    er[k] = (i < V) ? __expf(er[k] - zmax) : 0.0f;
+                    const float mine = er[k];
+#pragma unroll 1
+                    for (unsigned l = 0; l < 32 && 32u * k + l < V; l++) total += (double)__shfl_sync(0xffffffffu, mine, (int)l);
+                }
                 float best = -INFINITY;
                 unsigned best_i = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
+#pragma unroll 1
+                for (unsigned k = 0; k < 8; k++) {
                     const unsigned i = 32u * k + lane;
                     if (i < V) {
-                        const float hv = (float)((double)zr[k] / total);
+                        const float hv = (float)((double)er[k] / total);
                         if (!(best > hv)) { best = hv; best_i = i; }
                         if (i == ans_idx) h_true_v = hv;
                     }
