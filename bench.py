@@ -74,11 +74,15 @@ def workload(name: str, synth):
 def ncu_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full capture
     (profiles/r01_traffic.json; the launch it was taken on is named there).  None when there is no capture."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            return json.load(fh).get(kernel)
-    except OSError:
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                v = json.load(fh).get(kernel)
+            if v is not None:
+                return v
+        except OSError:
+            continue
+    return None
 
 
 def measured_peak():
@@ -227,26 +231,15 @@ def c5_cpu_rate(synth, cfg, weights, slots=1 << 16, queries=4):
     return 1.0 / per_query_full, dt, slots, queries
 
 
-def run_bigmem(args):
-    import torch
-    rank, world, local = dist_setup(args.gpus)
-    if world == 1 and args.gpus > 1:
-        print("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)", file=sys.stderr)
-        return 2
-    torch.cuda.set_device(local)
-    dev = f"cuda:{local}"
-    pkg = ge.import_package()
-    synth, qlib = pkg.synth, pkg.lib
+def c5_build(torch, synth, qlib, world, rank, dev, Q, group):
+    """This rank's slot shard of the synthetic 2^20 x 256 memory (generated on the device, shard by shard, from seeds that
+    depend only on (hop, slot block), so the global memory is the same for every world size), the queries and the object."""
     cfg = c5_config(synth)
-    Qs = [int(x) for x in str(args.queries).split(",") if x]
-    Q = max(Qs)
-    W, K = max(3, args.warmup), max(1, args.steps)
     weights = synth.make_weights(cfg, 0x5EED0000 + 5, sigma=0.3)
     f = cfg.formats()
     lo, n_loc = qlib.slot_shard(C5_S, world, rank)
-    # the memory is generated on the device, shard by shard, from a seed that depends only on (hop, slot block),
-    # so the global memory is the same for every world size
     BLK = 1 << 16
+
     def gen(kind, h):
         out = torch.empty((n_loc, cfg.d), dtype=torch.int8, device=dev)
         sc = (0.1 if kind == 0 else 0.5) * (1 << f["frac_w"][h])
@@ -265,12 +258,28 @@ def run_bigmem(args):
         r = (q * 104729 + 17) % C5_S
         if lo <= r < lo + n_loc:
             M8[0][r - lo] = (u0[q].to(torch.int32) * 2).clamp(-127, 127).to(torch.int8)
+    mem = qlib.BigMemory(cfg, weights, M8, C8, C5_S, lo, Q_max=Q, device=dev, group=group, world=world)
+    return cfg, weights, mem, u0, n_loc
+
+
+def run_bigmem(args):
+    import torch
+    rank, world, local = dist_setup(args.gpus)
+    if world == 1 and args.gpus > 1:
+        print("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    pkg = ge.import_package()
+    synth, qlib = pkg.synth, pkg.lib
+    Qs = [int(x) for x in str(args.queries).split(",") if x]
+    Q = max(Qs)
+    W, K = max(3, args.warmup), max(1, args.steps)
     group = None
     if world > 1:
         import torch.distributed as dist
         group = dist.group.WORLD
-    mem = qlib.BigMemory(cfg, weights, M8, C8, C5_S, lo, Q_max=Q, device=dev, group=group, world=world)
-    u0_all = u0
+    cfg, weights, mem, u0_all, n_loc = c5_build(torch, synth, qlib, world, rank, dev, Q, group)
     rc = 0
     for qi, Qn in enumerate(Qs):
         rc |= _bigmem_measure(args, torch, qlib, synth, cfg, weights, mem, u0_all[:Qn].contiguous(), Qn, W, K, rank, world, local, dev, n_loc,
@@ -280,6 +289,92 @@ def run_bigmem(args):
         dist.barrier()
         dist.destroy_process_group()
     return rc
+
+
+def c5_record(torch, synth, qlib, rank, world, local, Qs=(64, 1024), K=10, W=3):
+    """The slot-sharded large-memory workload (BASELINE configs[4], the one with a collective) measured inside the default
+    run so that the driver's per-N lines carry it: strong scaling (one 2^20 x 256 memory split over the ranks), queries/s at
+    Q = 64 and 1024, the scorer's share and the cost of the two per-hop all-reduces; at N > 1 the sharded predictions are
+    checked against an unsharded run of the same memory on rank 0 before anything is timed."""
+    dev = f"cuda:{local}"
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        group = dist.group.WORLD
+    Qmax = max(Qs)
+    cfg, weights, mem, u0, n_loc = c5_build(torch, synth, qlib, world, rank, dev, Qmax, group)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rec = {"workload": "C5: one pre-embedded memory of 2^20 slots, d=256, 3 hops, fixed-point dot attention, slot-sharded x%d "
+                       "(strong scaling); per hop all_reduce(SUM) of u32 score histograms [Q][255] and i32 partial reads [Q][256]" % world,
+           "slots_per_rank": int(n_loc), "scaling": "strong"}
+    if world > 1:
+        import torch.distributed as dist
+        pred_sh = mem.forward(u0)["pred"].cpu().numpy().copy()
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            _, _, full, u0f, _ = c5_build(torch, synth, qlib, 1, 0, dev, Qmax, None)
+            pred_full = full.forward(u0f)["pred"].cpu().numpy().copy()
+            full.close()
+            del full
+            ok[0] = int(np.array_equal(pred_sh, pred_full))
+        dist.broadcast(ok, src=0)
+        rec["sharded_equals_unsharded"] = bool(int(ok[0]))
+        assert rec["sharded_equals_unsharded"], "slot-sharded predictions differ from the unsharded memory"
+        torch.cuda.empty_cache()
+    for Q in Qs:
+        uq = u0[:Q].contiguous()
+        for _ in range(W):
+            mem.forward(uq)
+        barrier()
+        mem.profile(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(K):
+            mem.forward(uq)
+            mem.profile_read()
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1) / K
+        ms_scores, n_scores = mem.profile_read(reset=True)
+        mem.profile(False)
+        # the two per-hop exchanges alone, same payloads, same stream
+        ar_ms = 0.0
+        if world > 1:
+            import torch.distributed as dist
+            hist, part = mem.hist[:Q], mem.partial[:Q]
+            for _ in range(3):
+                dist.all_reduce(hist); dist.all_reduce(part)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(K * cfg.H):
+                dist.all_reduce(hist); dist.all_reduce(part)
+            a1.record(stream)
+            barrier()
+            ar_ms = a0.elapsed_time(a1) / K
+            hist.zero_(); part.zero_()
+        t = torch.tensor([ms, ms_scores / max(1, n_scores), ar_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, sc_ms, ar_ms = float(t[0]), float(t[1]), float(t[2])
+        peak, _ = measured_peak()
+        rec[f"q{Q}"] = {"queries_per_s": Q / (ms / 1e3), "ms_per_step": ms, "scorer_ms_per_launch": sc_ms,
+                        "scorer_launches_per_step": n_scores / K, "allreduce_ms_per_step": ar_ms,
+                        "scorer_GB/s": n_loc * cfg.d / (sc_ms / 1e3) / 1e9 if sc_ms > 0 else None,
+                        "scorer_frac_of_hbm": (n_loc * cfg.d / (sc_ms / 1e3) / 1e9 / peak) if sc_ms > 0 else None}
+    mem.close()
+    del mem
+    torch.cuda.empty_cache()
+    return rec
 
 
 def _bigmem_measure(args, torch, qlib, synth, cfg, weights, mem, u0, Q, W, K, rank, world, local, dev, n_loc, cpu_wanted):
@@ -449,12 +544,37 @@ def run_reference(args):
     return 0
 
 
+def run_reference_gpu(args):
+    """--impl reference_gpu: the reference's OWN CUDA forward (unmodified lib/layer.c + lib/layer_cuda.cu rebuilt for sm_100a by
+    oracle/Makefile, one story per 31 launches) on this box's GPU 0, on a bounded sample of the workload."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    pkg = ge.import_package()
+    synth = pkg.synth
+    if args.workload not in ("C1", "C2", "C3"):
+        print(json.dumps({"impl": "reference_gpu", "unavailable": "the reference cannot launch this shape (dimensions above 1024 / no such preset)"}), flush=True)
+        return 0
+    cfg, n, S, desc = workload(args.workload, synth)
+    w = synth.make_weights(cfg, 0x5EED0000 + 1, sigma=SIGMA)
+    sample = 2000
+    r = reference_gpu_rate(synth, cfg, w, S, sample=sample, reps=max(1, min(args.steps, 3)))
+    if not r or "unavailable" in r:
+        print(json.dumps({"impl": "reference_gpu", "unavailable": (r or {}).get("unavailable", "oracle/_ref/ref_harness_refcuda was not built")}), flush=True)
+        return 0
+    print(json.dumps({
+        "impl": "reference_gpu", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["s_per_pass"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}; {sample}-story sample per step", "kind": r["kind"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 31 * sample}), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference_gpu"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--queries", type=str, default="64",
                     help="C5: queries per step; a comma list (e.g. 1,64,1024) runs them one after the other on the same resident memory "
@@ -464,9 +584,12 @@ def main():
                          "built from (SURVEY 8f-1, reported separately, never mixed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
+    ap.add_argument("--quick", action="store_true", help="headline only: no sensitivity / e2e_ids / c5 / reference_gpu sections (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference_gpu":
+        return run_reference_gpu(args)
     if args.workload == "C5":
         return run_bigmem(args)
 
@@ -503,6 +626,7 @@ def main():
     for _ in range(W):
         model.forward(db, with_answers=False)
     barrier()
+    model.path_counts()                 # reset the tier counters: the timed region alone is counted
     model.profile(True)
     model.profile_read()
     sampler = ClockSampler(local)
@@ -530,6 +654,7 @@ def main():
     launches = qlib.lib().qmann_launch_count() - launches0
     ms_compact, ms_forward, pairs = model.profile_read()
     model.profile(False)
+    tiers = model.path_counts()
     # keep the GPU busy a little longer if the timed region was too short for the 100 ms sampler
     t_end = time.time() + max(0.0, 0.6 - ms_total / 1e3)
     while time.time() < t_end:
@@ -564,14 +689,70 @@ def main():
     assert match_h == int((pred_h == st.ans).sum())
     d2h = int(4 * n + 4)
 
+    # ---------------- the same step with weights that saturate more (which tier finishes how many stories) ----------------
+    def timed_steps(mdl, dbatch, k):
+        for _ in range(3):
+            mdl.forward(dbatch, with_answers=False)
+        torch.cuda.synchronize()
+        mdl.path_counts()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            mdl.forward(dbatch, with_answers=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t3 = mdl.path_counts()
+        tot = max(1, k * n)
+        return e0.elapsed_time(e1) / k, {"packed": t3[0] / tot, "unpacked": t3[1] / tot, "general": t3[2] / tot}
+    sensitivity = {}
+    if not use_ids and not args.quick:
+        for sg in (1.0, 2.0):
+            w2 = synth.make_weights(cfg, 0x5EED0000 + 1, sigma=sg)
+            m2 = qlib.Model(cfg, w2, device=f"cuda:{local}")
+            ms2, share2 = timed_steps(m2, db, max(3, K // 2))
+            sensitivity[f"sigma_{sg:g}"] = {"ms_per_step": ms2, "stories_per_s_per_gpu": n / (ms2 / 1e3), "path_share": share2}
+            m2.close()
+
+    # ---------------- end to end with the word-id lists (separate figure, never mixed with the headline) ----------------
+    e2e_ids = None
+    if not use_ids and not args.quick:
+        ist2 = synth.ids_from_dense(st)
+        ids_pin = torch.from_numpy(ist2.ids.view(np.int16)).pin_memory().numpy().view(np.uint16)
+        off_pin = torch.from_numpy(ist2.row_off.view(np.int32)).pin_memory().numpy().view(np.uint32)
+        ans_pin = torch.from_numpy(ist2.ans.astype(np.uint32).view(np.int32)).pin_memory().numpy().view(np.uint32)
+        for _ in range(2):
+            p_i, m_i, _ = model.infer_ids_host(ids_pin, off_pin, ans_pin, st.n_sen)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            p_i, m_i, _ = model.infer_ids_host(ids_pin, off_pin, ans_pin, st.n_sen)
+        torch.cuda.synchronize()
+        ids_ms = 1e3 * (time.perf_counter() - t0) / Ke
+        assert np.array_equal(p_i, pred_dev), "word-id input predicts differently from the dense input"
+        e2e_ids = {"ms_per_step": ids_ms, "h2d_bytes_per_step": int(ist2.ids.nbytes + ist2.row_off.nbytes + ist2.ans.nbytes), "d2h_bytes_per_step": d2h}
+        del ist2
+
+    # ---------------- the workload with a collective: slot-sharded large memory, same process group ----------------
+    c5 = None
+    if not use_ids and not args.quick and args.workload == "C2":
+        try:
+            c5 = c5_record(torch, synth, qlib, rank, world, local, K=max(4, min(K, 10)))
+        except AssertionError:
+            raise
+        except Exception as e:          # noqa: BLE001  (an allocation failure must not lose the headline line)
+            c5 = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
     # ---------------- max over ranks ----------------
     ms_step = ms_total / K
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms_step, e2e_ms, ms_compact / max(1, pairs), ms_forward / max(1, pairs)], dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([ms_step, e2e_ms, ms_compact / max(1, pairs), ms_forward / max(1, pairs), e2e_ids["ms_per_step"] if e2e_ids else 0.0],
+                         dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, e2e_ms = float(t[0]), float(t[1])
         k_compact_ms, k_forward_ms = float(t[2]), float(t[3])
+        if e2e_ids:
+            e2e_ids["ms_per_step"] = float(t[4])
     else:
         k_compact_ms, k_forward_ms = ms_compact / max(1, pairs), ms_forward / max(1, pairs)
 
@@ -587,30 +768,44 @@ def main():
         peak, peak_src = measured_peak()
         launches_per_step = pairs / K
         stories_per_launch = n / max(1.0, launches_per_step)
-        dom = "k_forward" if k_forward_ms >= k_compact_ms else "k_compact"
-        dom_ms = max(k_forward_ms, k_compact_ms)
-        achieved = bytes_story * stories_per_launch / (dom_ms / 1e3) / 1e9
-        # ncu captures exist for the default workload only (C2, 20 000 stories per launch)
-        cap = {k: ncu_traffic(k) for k in ("k_compact", "k_forward_fast", "k_ids_compact")} if (args.workload == "C2" and stories_per_launch == 20000) else {}
+        step_bytes = bytes_story * n                      # algorithmic bytes one rank moves per step
+        tc_tier = os.environ.get("QMANN_TC") == "1"
+        # Whole-step fraction: the number north_star's ">= 60 % of the HBM roofline" is held against.  The two kernels of a step
+        # bind on different resources: k_compact streams the dense arenas once (HBM-bound), the forward tiers read only the
+        # compact records (L2) and are bound by instruction issue.
+        whole = step_bytes / (ms_step / 1e3) / 1e9
+        cap = {k: ncu_traffic(k) for k in ("k_compact", "k_story", "k_story_tc", "k_ids_compact")} if (args.workload == "C2" and stories_per_launch == 20000) else {}
         tr = lambda k: (cap.get(k) or {}).get("dram_bytes_per_launch")
+        issue = (cap.get("k_story_tc" if tc_tier else "k_story") or {})
+        issue_slots = 148 * 4 * 1.965e9                   # warp instructions per second at one per scheduler and clock
+        fwd_inst = issue.get("warp_instructions_per_launch")
+        kernels = {
+            "k_compact": {"ms": k_compact_ms, "bound": "hbm", "GB/s": step_bytes / (k_compact_ms / 1e3) / 1e9 if k_compact_ms > 0.01 else None,
+                          "frac_of_hbm": (step_bytes / (k_compact_ms / 1e3) / 1e9 / peak) if k_compact_ms > 0.01 else None,
+                          "dram_bytes_per_launch_ncu": tr("k_ids_compact" if use_ids else "k_compact")},
+            "forward_tiers": {"ms": k_forward_ms, "bound": "instruction issue",
+                              "kernel": ("k_story_tc (tcgen05 embedding; it also streams the dense rows, there is no k_compact pass)" if tc_tier else
+                                         "k_story<packed> -> k_story<unpacked> -> k_forward on what each declines"),
+                              "warp_instructions_per_launch_ncu": fwd_inst,
+                              "issue_slot_frac": (fwd_inst / (issue_slots * k_forward_ms / 1e3)) if (fwd_inst and k_forward_ms > 0) else None,
+                              "dram_bytes_per_launch_ncu": tr("k_story_tc" if tc_tier else "k_story")},
+        }
+        dom = "forward_tiers" if k_forward_ms >= k_compact_ms else "k_compact"
         roofline = {
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": tr("k_forward_fast") if dom == "k_forward" else tr("k_ids_compact" if use_ids else "k_compact"),
-            "traffic_note": "dram bytes of one launch of the dominant kernel from profiles/r01_ncu_summary.txt; k_forward_fast reads only the "
-                            "compact records (L2 misses), the dense input is read once by k_compact: "
-                            f"{tr('k_ids_compact' if use_ids else 'k_compact')} B per launch vs {bytes_story * stories_per_launch:.0f} algorithmic",
-            "kernel": dom, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
+            "bound": "hbm", "achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
+            "traffic": (tr("k_story_tc") if tc_tier else ((tr("k_ids_compact" if use_ids else "k_compact") or 0) + (tr("k_story") or 0)) or None),
+            "traffic_note": "dram read+write bytes of one step from the committed ncu --set full captures (profiles/r02_traffic.json), all kernels of "
+                            f"the step; algorithmic bytes of the step {step_bytes:.0f}",
+            "scope": "whole step: algorithmic bytes of the step / step time (CUDA events over the timed region)",
+            "dominant_kernel": dom, "kernels": kernels, "peak_source": peak_src, "frac_of_nominal_8TBs": whole / NOMINAL_HBM_GBS,
             "algorithmic_bytes_per_story": bytes_story, "stories_per_launch": stories_per_launch,
-            "kernels": {
-                "k_compact": {"ms": k_compact_ms, "GB/s": bytes_story * stories_per_launch / (k_compact_ms / 1e3) / 1e9},
-                "k_forward": {"ms": k_forward_ms, "GB/s": bytes_story * stories_per_launch / (k_forward_ms / 1e3) / 1e9},
-            },
-            "whole_step_GB/s": bytes_story * n / (ms_step / 1e3) / 1e9,
-            "whole_step_frac": bytes_story * n / (ms_step / 1e3) / 1e9 / peak,
         }
         if use_ids:
             roofline["note"] = ("word-id input: ~0.6 KB per story, so the HBM roofline is out of reach by construction; the step is "
                                 "bound by the instruction issue rate of k_forward_fast (profiles/: smsp__issue_active)")
+        ref_gpu = None
+        if world == 1 and not args.quick and not use_ids and args.workload in ("C1", "C2", "C3"):
+            ref_gpu = reference_gpu_rate(synth, cfg, weights, S, sample=1000, reps=1)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             probe, _, threads, _ = cpu_oracle_rate(synth, cfg, weights, S, 64)
@@ -636,6 +831,15 @@ def main():
                             "qmann_infer_host (pinned host arenas in, host predictions + match count out)")},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "path_share": {"packed": tiers[0] / max(1, K * n), "unpacked": tiers[1] / max(1, K * n), "general": tiers[2] / max(1, K * n),
+                           "note": "share of the stories of the timed region that ENTERED each forward tier on rank 0 (a tier hands what it declines to the next)"},
+            "sensitivity": sensitivity or None,
+            "e2e_ids": ({"value": total_stories / (e2e_ids["ms_per_step"] / 1e3), "unit": UNIT, "ms_per_step": e2e_ids["ms_per_step"],
+                         "h2d_bytes_per_step": e2e_ids["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e_ids["d2h_bytes_per_step"],
+                         "api": "qmann_infer_ids_host (pinned host word-id lists in, host predictions out; SURVEY 8f-1 input format, not the headline)"}
+                        if e2e_ids else None),
+            "c5": c5,
+            "reference_gpu": ref_gpu,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "accuracy_check": {"match": int(match_h), "stories": n},
