@@ -584,6 +584,7 @@ def main():
                          "built from (SURVEY 8f-1, reported separately, never mixed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
+    ap.add_argument("--stories", type=int, default=0, help="C1-C4: stories per GPU and step (default: the workload's own count); BASELINE configs[3] sweeps 2^10 .. 2^20")
     ap.add_argument("--quick", action="store_true", help="headline only: no sensitivity / e2e_ids / c5 / reference_gpu sections (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -602,6 +603,8 @@ def main():
     pkg = ge.import_package()
     synth, qlib = pkg.synth, pkg.lib
     cfg, n, S, desc = workload(args.workload, synth)
+    if args.stories > 0:
+        n = args.stories
     W = max(3, args.warmup)
     K = max(1, args.steps)
 
@@ -614,7 +617,8 @@ def main():
     stream = torch.cuda.current_stream()
     # the id lists of a step (~16 MB) fit the 126 MB L2: evict them between timed steps by writing a 512 MB buffer
     # (outside the per-step events); the dense arenas (1 GB) are larger than L2 and need no flush
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local}") if use_ids else None
+    small = (4 * cfg.V * (S + 1) * n) < (200 << 20)      # inputs that fit the 126 MB L2: evict them between timed steps
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local}") if (use_ids or small) else None
 
     def barrier():
         if world > 1:
@@ -635,7 +639,7 @@ def main():
     launches0 = qlib.lib().qmann_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    if use_ids:
+    if use_ids or small:
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         for a_, b_ in evs:
             flush.zero_()
@@ -769,6 +773,7 @@ def main():
         launches_per_step = pairs / K
         stories_per_launch = n / max(1.0, launches_per_step)
         step_bytes = bytes_story * n                      # algorithmic bytes one rank moves per step
+        launch_bytes = bytes_story * stories_per_launch   # ... and per launch (batches above the chunk size run several launches per step)
         tc_tier = os.environ.get("QMANN_TC") == "1"
         # Whole-step fraction: the number north_star's ">= 60 % of the HBM roofline" is held against.  The two kernels of a step
         # bind on different resources: k_compact streams the dense arenas once (HBM-bound), the forward tiers read only the
@@ -780,8 +785,8 @@ def main():
         issue_slots = 148 * 4 * 1.965e9                   # warp instructions per second at one per scheduler and clock
         fwd_inst = issue.get("warp_instructions_per_launch")
         kernels = {
-            "k_compact": {"ms": k_compact_ms, "bound": "hbm", "GB/s": step_bytes / (k_compact_ms / 1e3) / 1e9 if k_compact_ms > 0.01 else None,
-                          "frac_of_hbm": (step_bytes / (k_compact_ms / 1e3) / 1e9 / peak) if k_compact_ms > 0.01 else None,
+            "k_compact": {"ms": k_compact_ms, "bound": "hbm", "GB/s": launch_bytes / (k_compact_ms / 1e3) / 1e9 if k_compact_ms > 0.01 else None,
+                          "frac_of_hbm": (launch_bytes / (k_compact_ms / 1e3) / 1e9 / peak) if k_compact_ms > 0.01 else None,
                           "dram_bytes_per_launch_ncu": tr("k_ids_compact" if use_ids else "k_compact")},
             "forward_tiers": {"ms": k_forward_ms, "bound": "instruction issue",
                               "kernel": ("k_story_tc (tcgen05 embedding; it also streams the dense rows, there is no k_compact pass)" if tc_tier else
@@ -823,7 +828,7 @@ def main():
                                         "into the dense arenas), resident in HBM") if use_ids else
                                        "dense fp32 bag-of-words arenas (reference boundary format), resident in HBM",
                        "l2": (f"inputs {bytes_story * n / 1e6:.0f} MB per step < 126 MB L2: a 512 MB buffer is written between timed steps "
-                              "(outside the per-step CUDA events) to evict them") if use_ids else
+                              "(outside the per-step CUDA events) to evict them") if (use_ids or small) else
                              f"inputs {bytes_story * n / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
