@@ -200,6 +200,16 @@ typedef struct qmann_batch qmann_batch;   /* per-story sentence counts / offsets
 int  qmann_model_create(qmann_model **out, const qmann_config *cfg, const qmann_weights *w);
 void qmann_model_destroy(qmann_model *m);
 
+/* Weight files in the layout of the reference driver's own raw dumps (MemN2N/MemN2N.c:2553-2618 load, :2853-2978 dump; the loops
+ * are commented out upstream): per file, per hop, for each input column j, for each output row i, one little-endian fp32
+ * w_mat[i][j] -- w_emb_a_float.bin (A, [d][V] x H), w_emb_c_float.bin (C), w_emb_q_float.bin (B), w_float.bin (W, [V][d]) and, in
+ * the same convention, w_lin_map_float.bin ([d][d] x H; required when cfg->lin_map).
+ * qmann_model_load() replaces those read loops plus the cuda_dense_init / cuda_dense_mat_init uploads (lib/layer.c:1790, :2600);
+ * qmann_weights_dump() writes the files from the fp32 device tensors of the layer structs. */
+int  qmann_model_load(qmann_model **out, const qmann_config *cfg, const char *dir);
+int  qmann_weights_dump(const qmann_config *cfg, const qmann_weights *w, const char *dir);
+const char *qmann_weights_last_error(void);
+
 /* Describe a packed batch: n_sen[i] sentences for story i (host array, like n_sen_test_arr,
  * MemN2N.c:2294-2333).  Uploads the offsets once. */
 int  qmann_batch_create(qmann_batch **out, const uint32_t *n_sen, uint32_t N);

@@ -68,6 +68,11 @@ def lib() -> C.CDLL:
     L.qmann_model_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(QConfig), C.POINTER(QWeights)]
     L.qmann_model_destroy.restype = None
     L.qmann_model_destroy.argtypes = [C.c_void_p]
+    L.qmann_model_load.restype = C.c_int
+    L.qmann_model_load.argtypes = [C.POINTER(C.c_void_p), C.POINTER(QConfig), C.c_char_p]
+    L.qmann_weights_dump.restype = C.c_int
+    L.qmann_weights_dump.argtypes = [C.POINTER(QConfig), C.POINTER(QWeights), C.c_char_p]
+    L.qmann_weights_last_error.restype = C.c_char_p
     L.qmann_batch_create.restype = C.c_int
     L.qmann_batch_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_U32), _U32]
     L.qmann_batch_destroy.restype = None
@@ -170,6 +175,32 @@ class Model:
         self._h = C.c_void_p()
         qc = make_config(cfg)
         _check(lib().qmann_model_create(C.byref(self._h), C.byref(qc), C.byref(qw)))
+
+    @classmethod
+    def from_weight_dir(cls, cfg, directory: str, device: str = "cuda:0") -> "Model":
+        """Model from the reference driver's raw weight files (qmann_model_load, MemN2N/MemN2N.c:2553-2618 layout)."""
+        import torch
+        self = cls.__new__(cls)
+        self.torch, self.cfg, self.device, self.w = torch, cfg, torch.device(device), {}
+        torch.cuda.set_device(self.device)
+        self._h = C.c_void_p()
+        qc = make_config(cfg)
+        rc = lib().qmann_model_load(C.byref(self._h), C.byref(qc), directory.encode())
+        if rc != 0:
+            raise QmannError(f"qmann_model_load error {rc}: {lib().qmann_weights_last_error().decode()}")
+        return self
+
+    def dump_weights(self, directory: str):
+        """The fp32 device weights this model was created from, written in the reference's dump layout (qmann_weights_dump)."""
+        qw = QWeights()
+        qw.dev_B, qw.dev_W = self.w["B"].data_ptr(), self.w["W"].data_ptr()
+        for h in range(self.cfg.H):
+            qw.dev_A[h], qw.dev_C[h], qw.dev_Hm[h] = self.w["A"][h].data_ptr(), self.w["C"][h].data_ptr(), self.w["Hm"][h].data_ptr()
+        qc = make_config(self.cfg)
+        os.makedirs(directory, exist_ok=True)
+        rc = lib().qmann_weights_dump(C.byref(qc), C.byref(qw), directory.encode())
+        if rc != 0:
+            raise QmannError(f"qmann_weights_dump error {rc}: {lib().qmann_weights_last_error().decode()}")
 
     def close(self):
         if self._h:

@@ -72,3 +72,22 @@ def test_formats_follow_reference_driver(qmann):
     assert f["iwl"] == [5, 5, 5] and f["frac"] == [2, 2, 2] and (f["iwl_bin"], f["frac_bin"]) == (5, 2)
     qc = qmann.lib.make_config(cfg)
     assert qc.V == 256 and qc.d == 50 and qc.S_max == 64 and list(qc.iwl_w)[:3] == [6, 5, 4]
+
+
+def test_unmodified_reference_driver_links_against_our_library():
+    """oracle/Makefile `ref_driver_link`: the reference's own MemN2N.o + sample.o + layer.o + common.o link against
+    libqmann_b200.so with --no-undefined, so every cuda_* symbol the driver and the layer code reference (66) is
+    resolved by the linker.  Needs the reference sources (build container only)."""
+    import subprocess
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir("/root/reference/MemN2N"):
+        pytest.skip("reference sources not mounted")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref_driver_link"])
+    assert os.path.exists(os.path.join(ref_dir, "memn2n_b200"))
+    need = set()
+    for obj in ("MemN2N.o", "layer.o"):
+        out = subprocess.run(["nm", "-u", os.path.join(ref_dir, obj)], capture_output=True, text=True, check=True).stdout
+        need |= {ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("cuda_")}
+    have = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "q-mann_b200", "libqmann_b200.so")], capture_output=True, text=True, check=True).stdout
+    have = {ln.split()[-1] for ln in have.splitlines() if ln.split()}
+    assert len(need) >= 60 and need <= have, sorted(need - have)

@@ -280,3 +280,83 @@ def test_packed_path_equals_unpacked_and_instrumented(preset, sigma, qmann, synt
     for tag in ("unpacked", "general"):
         np.testing.assert_array_equal(res["packed"][0], res[tag][0], err_msg=tag)
         assert res["packed"][1] == res[tag][1]
+
+
+def test_optional_layer_variants_match_reference_library_live(qmann):
+    """the optional, default-off variants on the same cuda_* surface -- scale layer (EN_SC_ATT,
+    lib/layer_cuda.cu:4805), activation layer (EN_NON_LINEARITY, :4548; NULL / SIGMOID / RELU, quantised and fp32),
+    shift-based softmax (:2038), attention mode 1 (pure fp32 dot products, lib/layer.c:177-195: scorer and transposed
+    read with f_fixed = false) -- entry point by entry point against the compiled reference (oracle/_ref/libqmann_ref.so)
+    on random fp32 inputs including off-grid, saturating and negative-zero-producing values.  Bit-identical outputs."""
+    import ctypes as C
+    import torch
+    refp = os.path.join(ROOT, "oracle", "_ref", "libqmann_ref.so")
+    if not os.path.exists(refp):
+        pytest.skip("oracle/_ref/libqmann_ref.so not built")
+    R, O = C.CDLL(refp), qmann.lib.lib()
+    u32, b, fp = C.c_uint, C.c_bool, C.c_void_p
+    sigs = {
+        "cuda_scale_fwd": [fp, fp, fp, u32, b, u32, u32, u32, b],
+        "cuda_activation_fwd": [fp, fp, C.c_char_p, u32, b, u32, u32, u32],
+        "cuda_softmax_fwd": [fp, fp, fp, fp, fp, u32, b, b],
+        "cuda_dot_mat_vec_fwd": [fp, fp, fp, fp, u32, u32, b, b, u32, u32, u32, u32, u32, b],
+        "cuda_dense_fwd": [fp, fp, fp, fp, fp, u32, u32, C.c_char_p, b, u32, u32, u32, u32, u32, b],
+        "cuda_sum_vec_fwd": [fp, fp, fp, u32, b, u32, u32, u32, b],
+    }
+    for L in (R, O):
+        for n, s in sigs.items():
+            getattr(L, n).argtypes = s
+            getattr(L, n).restype = None
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rnd = lambda *s, sc=4.0: (torch.randn(*s, device="cuda", generator=g) * sc).contiguous()
+    S, d = 53, 37
+    checked = []
+
+    def both(name, fn):
+        outs = []
+        for L in (R, O):
+            outs.append(fn(L))
+            torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1]), f"{name}: max |diff| {(outs[0] - outs[1]).abs().max().item()}"
+        assert torch.isfinite(outs[0]).all() or name.startswith("softmax_shift"), name
+        checked.append(name)
+
+    x = rnd(S)
+    x[::7] = -0.1                                        # truncates to a negative zero in the quantised variants
+    x[3], x[4] = 40.0, -40.0                             # saturate (5,2)
+    for wv in (0.37, -2.5, 1.0):
+        wt = torch.tensor([wv], device="cuda")
+        for ff in (True, False):
+            def scale(L, wt=wt, ff=ff):
+                o = torch.zeros(S, device="cuda"); L.cuda_scale_fwd(x.data_ptr(), wt.data_ptr(), o.data_ptr(), S, ff, 5, 2, 3, False); return o
+            both(f"scale w={wv} fixed={ff}", scale)
+    for kind in (b"NULL", b"SIGMOID", b"RELU"):
+        for ff, iwl, frac in ((True, 5, 2), (True, 2, 5), (False, 5, 2)):
+            def act(L, kind=kind, ff=ff, iwl=iwl, frac=frac):
+                o = torch.zeros(S, device="cuda"); L.cuda_activation_fwd(x.data_ptr(), o.data_ptr(), kind, S, ff, iwl, frac, 3); return o
+            both(f"activation {kind.decode()} fixed={ff} ({iwl},{frac})", act)
+    for sc in (1.0, 6.0):
+        s_in = (rnd(S, sc=sc) * 4).round() / 4           # scores on the (5,2) grid, as the scorer produces them
+        for shift in (False, True):
+            def softmax(L, s_in=s_in, shift=shift):
+                o = torch.zeros(S, device="cuda"); mx = torch.zeros(1, device="cuda")
+                L.cuda_softmax_fwd(o.data_ptr(), s_in.data_ptr(), None, None, mx.data_ptr(), S, shift, False); return o
+            both(f"softmax_shift={shift} scale={sc}", softmax)
+    # attention mode 1: fp32 scorer and fp32 transposed read (f_fixed = false), and the fp32 update
+    M, u, pv = rnd(S, d), rnd(d), torch.rand(S, device="cuda", generator=g)
+    def score_f(L):
+        o = torch.zeros(S, device="cuda"); L.cuda_dot_mat_vec_fwd(M.data_ptr(), u.data_ptr(), o.data_ptr(), None, S, d, False, False, 5, 2, 5, 2, 3, False); return o
+    def read_f(L):
+        o = torch.zeros(d, device="cuda"); L.cuda_dot_mat_vec_fwd(M.data_ptr(), pv.data_ptr(), o.data_ptr(), None, S, d, True, False, 5, 2, 5, 2, 3, False); return o
+    def sum_f(L):
+        o = torch.zeros(d, device="cuda"); L.cuda_sum_vec_fwd(u.data_ptr(), M[1].contiguous().data_ptr(), o.data_ptr(), d, False, 5, 2, 3, False); return o
+    both("mode-1 scorer (fp32)", score_f)
+    both("mode-1 read (fp32)", read_f)
+    both("fp32 update", sum_f)
+    # dense layer with an activation name, as EN_NON_LINEARITY wires it (activation argument of cuda_dense_fwd)
+    Wm, xv = rnd(d, S, sc=1.0), rnd(S)
+    for kind in (b"NULL", b"SIGMOID", b"RELU"):
+        def dense_act(L, kind=kind):
+            o = torch.zeros(d, device="cuda"); L.cuda_dense_fwd(Wm.data_ptr(), None, xv.data_ptr(), o.data_ptr(), None, S, d, kind, True, 5, 2, 5, 2, 3, False); return o
+        both(f"dense activation={kind.decode()}", dense_act)
+    assert len(checked) >= 25

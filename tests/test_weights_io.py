@@ -39,3 +39,39 @@ def test_weight_files_round_trip_and_layout(tmp_path, qmann, synth):
         io.load_weights(str(tmp_path), cfg)
     z = io.load_weights(str(tmp_path), cfg, require_lin_map=False)
     assert all(not h.any() for h in z.Hm)
+
+
+@pytest.mark.gpu
+def test_c_loader_and_dumper_on_the_device(qmann, synth, tmp_path):
+    """qmann_model_load (C): a model built from the reference-layout files predicts exactly like the model built from the
+    in-memory tensors (every intermediate of the instrumented pass identical); qmann_weights_dump writes byte-identical files."""
+    import torch
+    for preset, lin_map in (("C1", True), ("C2", True), ("C4", False)):
+        cfg = synth.preset_config(preset, lin_map=lin_map)
+        w = synth.make_weights(cfg, 5, sigma=0.5)
+        st = synth.make_stories(cfg, 300, 6, S=min(cfg.S_max, 50), ragged=True)
+        d1, d2 = str(tmp_path / f"{preset}_py"), str(tmp_path / f"{preset}_c")
+        qmann.weights_io.save_weights(d1, cfg, w)
+        m_mem = qmann.lib.Model(cfg, w)
+        m_file = qmann.lib.Model.from_weight_dir(cfg, d1)
+        outs = []
+        for m in (m_mem, m_file):
+            db = m.upload(st)
+            o = m.forward(db, with_answers=True, want_h=True, debug=True)
+            torch.cuda.synchronize()
+            outs.append({k: v.cpu().numpy().copy() for k, v in o.items() if hasattr(v, "cpu")})
+            p = m.forward(db, with_answers=True)          # production tiers
+            torch.cuda.synchronize()
+            outs[-1]["pred_prod"] = p["pred"].cpu().numpy()[:st.N].copy()
+        for k in outs[0]:
+            np.testing.assert_array_equal(outs[0][k], outs[1][k], err_msg=f"{preset}: {k}")
+        m_mem.dump_weights(d2)
+        for name in sorted(os.listdir(d1)):
+            assert open(os.path.join(d1, name), "rb").read() == open(os.path.join(d2, name), "rb").read(), name
+    # a file of the wrong size is refused with a message, not read past its end
+    bad = str(tmp_path / "bad")
+    qmann.weights_io.save_weights(bad, cfg, w)
+    with open(os.path.join(bad, "w_float.bin"), "ab") as fh:
+        fh.write(b"\0\0\0\0")
+    with pytest.raises(qmann.lib.QmannError):
+        qmann.lib.Model.from_weight_dir(cfg, bad)
