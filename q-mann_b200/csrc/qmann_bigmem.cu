@@ -29,6 +29,7 @@
 // histogram makes that a single exact collective and the result independent of the number of shards.
 #include "qmann_fixed.cuh"
 #include "qmann_common.h"
+#include "qmann_tc.cuh"
 #include "../../include/qmann_abi.h"
 
 #include <algorithm>
@@ -601,6 +602,348 @@ __global__ void __launch_bounds__(256) k_big_prep_bfrag(const signed char *__res
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// k_big_scores_tc: the same four int8 contractions on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in
+// tensor memory), d % 128 == 0.
+//
+//   4 * sum_t trunc0(y_t u_t / 4) = sum_t y_t u_t + sum_{a=1..3} sum_t I_a(y_t) * (-R_a(u_t))          (see k_big_scores_mma)
+//
+// One persistent CTA per SM and query block of 64.  Per tile of 128 slots and 128-byte K chunk:
+//   producer thread : TMA box (128 bytes x 128 rows, 128-byte swizzle) of Y -> stage;  Y itself is plane 0 of the A operand
+//   12 builder warps: the three indicator planes of every 16-byte chunk, written at the SAME offset of three more tiles (the map is
+//                     elementwise, so the swizzled layout carries over), then fence.proxy.async so that the tensor core sees them
+//   MMA thread      : 4 planes x 4 K steps of tcgen05.mma M128 N64 K32 into ONE accumulator tile (the query planes of a = 1..3
+//                     are stored negated); tcgen05.commit frees the stage, and after the last chunk hands the tile to the epilogue
+//   8 epilogue warps: (two per quadrant of tensor memory, 32 queries each) tcgen05.ld, (acc >> 2) clamped -> score bin per
+//                     (query, slot); entries whose products may saturate are recomputed product by product (same rule as the
+//                     other fast scorers)
+// Two stages, two accumulator tiles (2 x 64 TMEM columns).  The memory is streamed once per block of 64 queries.
+// -------------------------------------------------------------------------------------------------
+constexpr unsigned TCS_QB = 64, TCS_STAGES = 2, TCS_TILE = 128 * 128, TCS_BUILDERS = 12;
+constexpr unsigned TCS_EPI = 8;                       // epilogue warps: two per TMEM quadrant, 32 accumulator columns each
+// warp roles: the issue arbiter of an SM sub-partition favours the highest warp ids, so the epilogue (the critical path once the tensor
+// core is fed) gets them: builders first, then the producer, the MMA issuer, and the eight epilogue warps
+constexpr unsigned TCS_W_BUILD = 0, TCS_W_PROD = TCS_BUILDERS, TCS_W_MMA = TCS_BUILDERS + 1, TCS_W_EPI = TCS_BUILDERS + 2, TCS_WARPS = TCS_W_EPI + TCS_EPI;
+
+struct TcScoreParams {
+    alignas(64) CUtensorMap tmY;     // Y as bytes [S_local][d], box 128 x 128, 128-byte swizzle
+    const signed char *Y;
+    const unsigned char *rowmax;
+    unsigned long long S_local;
+    unsigned d, Q;
+    int la, fb;
+    const signed char *ub8;
+    const unsigned *umax;
+    const uint4 *bplanes;            // [qblocks][d/128][4 planes][64 rows x 128 B, swizzled]: the B operand's shared-memory image
+    void *bins;
+    int bin8;
+    unsigned bias;
+    unsigned long long *clk;         // QMANN_TC_TRACE builds: per-role cycle accumulators of CTA (0, 0)
+};
+#ifdef QMANN_TC_TRACE
+#define SCK_DECL unsigned long long sck[4] = {0ull, 0ull, 0ull, 0ull}; long long sck_t = clock64();
+#define SCK(i) do { const long long n_ = clock64(); sck[i] += (unsigned long long)(n_ - sck_t); sck_t = n_; } while (0)
+#define SCK_FLUSH(role) do { if (p.clk && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) for (int i_ = 0; i_ < 4; i_++) p.clk[(role) * 4 + i_] = sck[i_]; } while (0)
+#else
+#define SCK_DECL
+#define SCK(i) do { } while (0)
+#define SCK_FLUSH(role) do { } while (0)
+#endif
+
+// instruction descriptor of kind::i8: D int32 (bits 4-5 = 2), A and B signed 8-bit (bits 7-9, 10-12 = 1), K-major, N >> 3, M >> 4
+__host__ __device__ constexpr unsigned umma_idesc_i8(unsigned M, unsigned N) { return (2u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24); }
+__device__ __forceinline__ void umma_i8(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc, unsigned accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// one (slot, query) score in the reference order of operations: every product truncated and saturated before the sum
+__device__ __noinline__ int big_exact_score(const signed char *__restrict__ yr, const signed char *__restrict__ ur, unsigned d, int la, int fb)
+{
+    int sp = 0;
+#pragma unroll 4
+    for (unsigned t = 0; t < d; t++) sp += qi_mul((int)yr[t], (int)ur[t], la, fb);
+    return qi_clamp(sp, la);
+}
+
+__global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __grid_constant__ TcScoreParams p)
+{
+    using namespace qtc;
+    extern __shared__ __align__(16) unsigned char sm[];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned KC = p.d / 128;                                     // K chunks per tile
+    const unsigned sraw = smem_u32(sm), sbase = (sraw + 1023u) & ~1023u;
+    unsigned char *gbase = sm + (sbase - sraw);
+    // layout: [B planes: KC x 4 x 8 KB][stages: 2 x 4 planes x 16 KB][control, 512 B][two score-bin tiles of 64 x 128 bytes]
+    const unsigned bsm = sbase, stg = bsm + KC * 4u * 8192u, cb = stg + TCS_STAGES * 4u * TCS_TILE;
+    unsigned char *cbg = gbase + (cb - sbase);
+    const unsigned bar_full = cb, bar_built = cb + 16, bar_empty = cb + 32, bar_dfull = cb + 48, bar_dfree = cb + 64, tmem_slot = cb + 80;
+    unsigned *umax_s = reinterpret_cast<unsigned *>(cbg + 128);
+    const unsigned q0 = blockIdx.y * TCS_QB;
+    {
+        const uint4 *src = p.bplanes + (size_t)blockIdx.y * (KC * 4u * 8192u / 16u);
+        uint4 *dst = reinterpret_cast<uint4 *>(gbase);
+        for (unsigned i = threadIdx.x; i < KC * 4u * 8192u / 16u; i += blockDim.x) dst[i] = src[i];
+        for (unsigned i = threadIdx.x; i < TCS_QB; i += blockDim.x) umax_s[i] = (q0 + i < p.Q) ? p.umax[q0 + i] : 0u;
+    }
+    if (threadIdx.x == 0) {
+        for (unsigned s = 0; s < TCS_STAGES; s++) {
+            mbar_init(bar_full + 8 * s, 1); mbar_init(bar_built + 8 * s, TCS_BUILDERS); mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_dfull + 8 * s, 1); mbar_init(bar_dfree + 8 * s, TCS_EPI);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&p.tmY);
+    }
+    if (warp == TCS_W_MMA) tmem_alloc(tmem_slot, 128);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // the B planes written above are read by the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *reinterpret_cast<const unsigned *>(cbg + 80);
+    const unsigned long long n_tiles = (p.S_local + 127ull) / 128ull;
+
+    if (warp == TCS_W_PROD) {
+        if (lane == 0) {
+            unsigned it = 0;
+            SCK_DECL
+            for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (unsigned kc = 0; kc < KC; kc++, it++) {
+                    const unsigned s = it % TCS_STAGES, ph = (it / TCS_STAGES) & 1u;
+                    SCK(1);
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    SCK(0);
+                    mbar_expect_tx(bar_full + 8 * s, TCS_TILE);
+                    tma_load_2d(stg + s * 4u * TCS_TILE, &p.tmY, (int)(128u * kc), (int)(tile * 128ull), bar_full + 8 * s);
+                }
+            SCK(1); SCK_FLUSH(0);
+        }
+    } else if (warp == TCS_W_MMA) {
+        if (lane == 0) {
+            const unsigned idesc = umma_idesc_i8(128, TCS_QB);
+            unsigned it = 0, tc = 0;
+            // descriptors of the 2 x 4 A tiles and of the B tiles are formed once; an MMA then only steps the start-address field
+            // (+2 per 32 bytes of K)
+            unsigned long long adesc[TCS_STAGES][4];
+#pragma unroll
+            for (unsigned s_ = 0; s_ < TCS_STAGES; s_++)
+#pragma unroll
+                for (unsigned pl = 0; pl < 4; pl++) adesc[s_][pl] = umma_desc_sw128(stg + (s_ * 4u + pl) * TCS_TILE);
+            const unsigned long long bdesc0 = umma_desc_sw128(bsm);
+            SCK_DECL
+            for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tc++) {
+                const unsigned buf = tc & 1u;
+                SCK(2);
+                mbar_wait(bar_dfree + 8 * buf, ((tc >> 1) & 1u) ^ 1u);
+                SCK(0);
+                tc_fence_after();
+                for (unsigned kc = 0; kc < KC; kc++, it++) {
+                    const unsigned s = it % TCS_STAGES, ph = (it / TCS_STAGES) & 1u;
+                    SCK(2);
+                    mbar_wait(bar_built + 8 * s, ph);
+                    SCK(1);
+                    tc_fence_after();
+#pragma unroll
+                    for (unsigned pl = 0; pl < 4; pl++) {
+                        const unsigned long long ad = (s == 0) ? adesc[0][pl] : adesc[1][pl];
+                        const unsigned long long bd = bdesc0 + (unsigned long long)((kc * 4u + pl) * (8192u >> 4));
+#pragma unroll
+                        for (unsigned j = 0; j < 4; j++) umma_i8(tmem + buf * TCS_QB, ad + 2ull * j, bd + 2ull * j, idesc, (kc | pl | j) ? 1u : 0u);
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_dfull + 8 * buf);
+            }
+            SCK(2); SCK_FLUSH(1);
+        }
+    } else if (warp < TCS_BUILDERS) {
+        const unsigned bt = threadIdx.x;                                   // 0 .. 255
+        unsigned it = 0;
+        SCK_DECL
+        for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (unsigned kc = 0; kc < KC; kc++, it++) {
+                const unsigned s = it % TCS_STAGES, ph = (it / TCS_STAGES) & 1u;
+                SCK(1);
+                mbar_wait(bar_full + 8 * s, ph);
+                SCK(0);
+                unsigned char *y0 = gbase + (stg - sbase) + (size_t)s * 4u * TCS_TILE;
+#pragma unroll
+                for (unsigned i = 0; i < (TCS_TILE / 16u + TCS_BUILDERS * 32u - 1u) / (TCS_BUILDERS * 32u); i++) {
+                    const unsigned off = 16u * (bt + i * TCS_BUILDERS * 32u);
+                    if (off >= TCS_TILE) break;
+                    const uint4 y = *reinterpret_cast<const uint4 *>(y0 + off);
+                    uint4 i1, i2, i3;
+                    indicator_planes(y.x, i1.x, i2.x, i3.x);
+                    indicator_planes(y.y, i1.y, i2.y, i3.y);
+                    indicator_planes(y.z, i1.z, i2.z, i3.z);
+                    indicator_planes(y.w, i1.w, i2.w, i3.w);
+                    *reinterpret_cast<uint4 *>(y0 + TCS_TILE + off) = i1;
+                    *reinterpret_cast<uint4 *>(y0 + 2u * TCS_TILE + off) = i2;
+                    *reinterpret_cast<uint4 *>(y0 + 3u * TCS_TILE + off) = i3;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_built + 8 * s);
+            }
+        SCK(1);
+        if (warp == TCS_W_BUILD) SCK_FLUSH(2);
+    } else {
+        // epilogue warps: warp w reads TMEM lanes 32 (w % 4) .. + 31 = slots 32 (w % 4) + lane of the tile; the two warps of a
+        // quadrant take accumulator columns 0-31 and 32-63 (queries of this block)
+        const int la = p.la;
+        const unsigned sat_lim = 4u * (unsigned)la + 3u;
+        const unsigned ew = warp - TCS_W_EPI, et = threadIdx.x - TCS_W_EPI * 32u;          // epilogue warp / thread index
+        const unsigned quad = warp & 3u, qh = 32u * (ew >> 2);
+        const unsigned tq = tmem + ((32u * quad) << 16);
+        const unsigned nq = (p.Q > q0 + qh) ? min(32u, p.Q - q0 - qh) : 0u;       // queries of this warp's half that exist
+        unsigned umax_all = 0;
+        for (unsigned i = 0; i < 32; i++) umax_all = max(umax_all, umax_s[qh + i]);
+        unsigned tc = 0;
+        SCK_DECL
+        // the row maximum of the NEXT tile's slot is loaded one tile ahead (its DRAM latency would otherwise sit between the
+        // accumulator load and the stores of every tile)
+        unsigned rm_next = 0;
+        {
+            const unsigned long long r0 = (unsigned long long)blockIdx.x * 128ull + 32u * quad + lane;
+            if (blockIdx.x < n_tiles && r0 < p.S_local) rm_next = (unsigned)p.rowmax[r0];
+        }
+        for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tc++) {
+            const unsigned buf = tc & 1u;
+            const unsigned long long row = tile * 128ull + 32u * quad + lane;
+            const bool ok = row < p.S_local;
+            const unsigned rm = rm_next;
+            {
+                const unsigned long long rn = row + (unsigned long long)gridDim.x * 128ull;
+                rm_next = (tile + gridDim.x < n_tiles && rn < p.S_local) ? (unsigned)p.rowmax[rn] : 0u;
+            }
+            const bool lane_risky = rm * umax_all > sat_lim;                   // some query may saturate a product of this slot
+            SCK(3);
+            mbar_wait(bar_dfull + 8 * buf, (tc >> 1) & 1u);
+            SCK(0);
+            tc_fence_after();
+            unsigned v[32];
+            {
+                unsigned v0[16], v1[16];
+                tmem_ld16(tq + buf * TCS_QB + qh, v0);
+                tmem_ld16(tq + buf * TCS_QB + qh + 16u, v1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; i++) { v[i] = v0[i]; v[16 + i] = v1[i]; }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_dfree + 8 * buf);                  // the accumulators are in registers: the tile is free
+            SCK(1);
+            // Score bins of this warp's 32 slots x 32 queries go through a shared-memory tile [64 queries][128 slots] so that the
+            // tile leaves as whole 128-byte lines (two 128-bit stores per thread) instead of 32 byte stores per lane; entries whose
+            // products may saturate are recomputed product by product first (the reference order of operations).
+            unsigned char *tileb = cbg + 512 + (tc & 1u) * 8192u;
+            const bool vec_ok = p.bin8 && (p.S_local % 16ull == 0ull) && (tile * 128ull + 128ull <= p.S_local);
+            unsigned risky = 0u;
+            if (ok && lane_risky) {
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    if ((unsigned)i < nq && rm * umax_s[qh + i] > sat_lim) risky |= 1u << i;
+            }
+            if (vec_ok) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) tileb[(qh + i) * 128u + 32u * quad + lane] = (unsigned char)(qi_clamp((int)v[i] >> 2, la) + (int)p.bias);      // exact: a multiple of 4
+            } else if (ok) {
+#pragma unroll 4
+                for (unsigned i = 0; i < nq; i++)
+                    if (!((risky >> i) & 1u)) store_bin(p.bins, p.bin8, (size_t)(q0 + qh + i) * p.S_local + row, (unsigned)(qi_clamp((int)v[i] >> 2, la) + (int)p.bias));
+            }
+            // (slot, query) pairs with a product that may saturate: the reference order of operations, product by product, by the
+            // whole warp (8 products per lane and 256 dims, one reduction per pair) -- a lane alone would stall its tile for
+            // thousands of instructions per pair
+            unsigned any = __ballot_sync(0xffffffffu, risky != 0u);
+            while (any) {
+                const int src = __ffs((int)any) - 1;
+                any &= any - 1u;
+                unsigned m = __shfl_sync(0xffffffffu, risky, src);
+                const signed char *yr = p.Y + (tile * 128ull + 32u * quad + (unsigned)src) * p.d;
+                while (m) {
+                    const unsigned i = (unsigned)(__ffs((int)m) - 1);
+                    m &= m - 1u;
+                    const signed char *ur = p.ub8 + (size_t)(q0 + qh + i) * p.d;
+                    int sp = 0;
+                    for (unsigned t0 = 8u * lane; t0 < p.d; t0 += 256u) {
+                        const uint2 yv = *reinterpret_cast<const uint2 *>(yr + t0), uv = *reinterpret_cast<const uint2 *>(ur + t0);
+#pragma unroll
+                        for (int b8 = 0; b8 < 4; b8++) {
+                            sp += qi_mul((int)(signed char)((yv.x >> (8 * b8)) & 0xFFu), (int)(signed char)((uv.x >> (8 * b8)) & 0xFFu), la, p.fb);
+                            sp += qi_mul((int)(signed char)((yv.y >> (8 * b8)) & 0xFFu), (int)(signed char)((uv.y >> (8 * b8)) & 0xFFu), la, p.fb);
+                        }
+                    }
+                    sp = __reduce_add_sync(0xffffffffu, sp);
+                    const unsigned code = (unsigned)(qi_clamp(sp, la) + (int)p.bias);
+                    if (lane == (unsigned)src) {
+                        if (vec_ok) tileb[(qh + i) * 128u + 32u * quad + lane] = (unsigned char)code;
+                        else store_bin(p.bins, p.bin8, (size_t)(q0 + qh + i) * p.S_local + row, code);
+                    }
+                }
+            }
+            SCK(2);
+            if (vec_ok) {
+                asm volatile("bar.sync 1, %0;" ::"n"(TCS_EPI * 32) : "memory");           // the eight epilogue warps
+                unsigned char *dst = reinterpret_cast<unsigned char *>(p.bins) + tile * 128ull;
+#pragma unroll
+                for (unsigned k = 0; k < 2; k++) {
+                    const unsigned idx = et + k * TCS_EPI * 32u;                            // 512 segments of 16 bytes
+                    const unsigned ql = idx >> 3, seg = idx & 7u;
+                    if (q0 + ql < p.Q)
+                        *reinterpret_cast<uint4 *>(dst + (size_t)(q0 + ql) * p.S_local + 16u * seg) = *reinterpret_cast<const uint4 *>(tileb + ql * 128u + 16u * seg);
+                }
+            }
+            SCK(3);
+        }
+        if (ew == 0) SCK_FLUSH(3);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == TCS_W_MMA) tmem_dealloc(tmem, 128);
+}
+
+// Query planes of k_big_scores_tc as the shared-memory image of its B operand: for query block qb, K chunk kc, plane pl: 64 rows
+// (queries) x 128 bytes with the 16-byte chunks XOR-swizzled by (row & 7) (the 128-byte swizzle of the K-major descriptor).
+// Plane 0 = Q_bin(u); planes a = 1..3 = -sgn(u) ((a (|u| & 3)) & 3) (negated: all four contractions accumulate into one tile).
+__global__ void __launch_bounds__(256) k_big_prep_bplanes(const signed char *__restrict__ ub8, unsigned Q, unsigned d, uint4 *__restrict__ out)
+{
+    const unsigned KC = d / 128, per_block = KC * 4u * 512u;              // uint4 per query block
+    const unsigned qblocks = (Q + TCS_QB - 1) / TCS_QB;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < qblocks * per_block; i += gridDim.x * blockDim.x) {
+        const unsigned qb = i / per_block, r = i % per_block;
+        const unsigned kc = r / 2048u, pl = (r / 512u) % 4u, row = (r / 8u) % 64u, pos = r % 8u;
+        const unsigned chunk = pos ^ (row & 7u);                         // logical 16-byte chunk stored at this position
+        const unsigned q = qb * TCS_QB + row;
+        unsigned w[4] = {0u, 0u, 0u, 0u};
+        if (q < Q) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                unsigned word = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int u = (int)ub8[(size_t)q * d + 128u * kc + 16u * chunk + 4u * j + t];
+                    int v = u;
+                    if (pl) {
+                        const int sg = (u > 0) - (u < 0);
+                        v = -sg * (int)(((unsigned)pl * ((unsigned)abs(u) & 3u)) & 3u);
+                    }
+                    word |= ((unsigned)v & 0xFFu) << (8 * t);
+                }
+                w[j] = word;
+            }
+        }
+        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // One warp per row: Y[r][t] = Q_att(M[r][t]) (written when Y != nullptr), rowmax[r] = max_t |Y[r][t]|, and *mismatch
 // is set when some Y differs from its M code (then the scorer needs the copy).
 __global__ void __launch_bounds__(256) k_big_prep_mem(const signed char *__restrict__ M, unsigned long long S, unsigned d, HopFmt f,
@@ -993,6 +1336,10 @@ struct qmann_bigmem {
     unsigned *umax;                  // [Q_max] max |Q_bin(u)|
     uint4 *bfrag;                    // k_big_scores_mma query planes, fragment order
     bool mma_ok;
+    // k_big_scores_tc (tcgen05): query planes as the B operand's shared-memory image, one tensor map of Y per hop
+    uint4 *bplanes;
+    bool tc_ok;
+    CUtensorMap tmY[MAXH];
     // k_big_scores_fast inputs per hop: Y = Q_att(M) (== M when the re-quantisation is the identity), row maxima
     const signed char *Y[MAXH];
     signed char *Y_own[MAXH];
@@ -1057,6 +1404,36 @@ static int dispatch_scores_fast(qmann_bigmem *b, const FastScoreParams &fp, cuda
     }
     return bfail(QMANN_E_ARG, "k_big_scores_fast: d/16 must be a power of two");
 }
+
+#ifdef QMANN_TC_TRACE
+static unsigned long long *g_tcs_clk = nullptr;
+extern "C" void qmann_bigmem_tc_trace_dump(void)
+{
+    if (!g_tcs_clk) return;
+    const char *roles[4] = {"producer (wait empty | issue)", "mma (wait dfree | wait built | issue)", "builder (wait full | build)", "epilogue (wait dfull | tmem ld | stores | risky+loop)"};
+    for (int r = 0; r < 4; r++) fprintf(stderr, "%-40s %12llu %12llu %12llu %12llu\n", roles[r], g_tcs_clk[4 * r], g_tcs_clk[4 * r + 1], g_tcs_clk[4 * r + 2], g_tcs_clk[4 * r + 3]);
+}
+#endif
+namespace {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda): byte matrix [rows][cols],
+// boxes of 128 bytes x 128 rows, 128-byte swizzle -- the A operand tiles of k_big_scores_tc
+bool tmap_bytes_rows(CUtensorMap *out, const void *base, unsigned long long rows, unsigned cols)
+{
+    typedef CUresult (*enc_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static enc_fn enc = []() -> enc_fn {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+        return (enc_fn)f;
+    }();
+    if (!enc || rows == 0 || ((uintptr_t)base % 16)) return false;
+    cuuint64_t dims[2] = {cols, rows}, strides[1] = {cols};
+    cuuint32_t box[2] = {128, 128}, es[2] = {1, 1};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
 
 extern "C" {
 
@@ -1169,6 +1546,16 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
         BCUDA(cudaDeviceSynchronize());
         cudaFree(dev_flag);
     }
+    {
+        // tcgen05 scorer: every fast hop's Y as a TMA tensor, the B planes' image; QMANN_BIGMEM_TC=0 keeps the mma.sync kernel
+        const char *env_tc = getenv("QMANN_BIGMEM_TC");
+        const size_t need = (size_t)(c.d / 128) * 4 * 8192 + (size_t)TCS_STAGES * 4 * TCS_TILE + 1024 + 512 + 2 * 8192;
+        bool ok = b->mma_ok && c.d % 128 == 0 && c.d >= 128 && need <= (size_t)b->smem_optin && !(env_tc && atoi(env_tc) == 0);
+        for (unsigned h = 0; h < c.H && ok; h++)
+            if (b->fast[h]) ok = tmap_bytes_rows(&b->tmY[h], b->Y[h], S_local, c.d);
+        if (ok) BCUDA(cudaMalloc((void **)&b->bplanes, (size_t)((Q_max + TCS_QB - 1) / TCS_QB) * (c.d / 128) * 4 * 8192));
+        b->tc_ok = ok;
+    }
     BCUDA(cudaDeviceSynchronize());
     *out = b;
     return QMANN_OK;
@@ -1178,7 +1565,7 @@ void qmann_bigmem_destroy(qmann_bigmem *b)
 {
     if (!b) return;
     cudaFree(b->u_a); cudaFree(b->u_b); cudaFree(b->ub); cudaFree(b->av); cudaFree(b->sv); cudaFree(b->bins);
-    cudaFree(b->ub8); cudaFree(b->umax); cudaFree(b->bfrag);
+    cudaFree(b->ub8); cudaFree(b->umax); cudaFree(b->bfrag); cudaFree(b->bplanes);
     for (int h = 0; h < MAXH; h++) { cudaFree(b->Y_own[h]); cudaFree(b->rowmax[h]); }
     cudaFree(b->pq); cudaFree(b->thr); cudaFree(b->nsel); cudaFree(b->zbuf);
     for (int h = 0; h < MAXH; h++) cudaFree(b->dev_H[h]);
@@ -1216,7 +1603,32 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
         int rc;
         const bool prof = b->profile && b->pused + 2 <= 2 * MAXH;
         if (prof) BCUDA(cudaEventRecord(b->pev[b->pused], st));
-        if (b->fast[h] && b->mma_ok && Q >= 4) {
+        if (b->fast[h] && b->tc_ok && Q >= 4) {
+            const unsigned qblocks = (Q + TCS_QB - 1) / TCS_QB, KC = d / 128;
+            k_big_prep_bplanes<<<std::min(512u, (qblocks * KC * 2048u + 255u) / 256u), 256, 0, st>>>(b->ub8, Q, d, b->bplanes);
+            count_launch();
+            TcScoreParams tp;
+            tp.tmY = b->tmY[h];
+            tp.Y = b->Y[h]; tp.rowmax = b->rowmax[h]; tp.S_local = b->S_local; tp.d = d; tp.Q = Q; tp.la = f.la; tp.fb = f.fb;
+            tp.ub8 = b->ub8; tp.umax = b->umax; tp.bplanes = b->bplanes; tp.bins = b->bins; tp.bin8 = b->bin8; tp.bias = (unsigned)f.la;
+            tp.clk = nullptr;
+#ifdef QMANN_TC_TRACE
+            static unsigned long long *clk_host = nullptr;
+            if (!clk_host) BCUDA(cudaHostAlloc((void **)&clk_host, 16 * 8, cudaHostAllocMapped));
+            { unsigned long long *dp = nullptr; BCUDA(cudaHostGetDevicePointer((void **)&dp, clk_host, 0)); tp.clk = dp; }
+            g_tcs_clk = clk_host;
+#endif
+            const size_t smem = (size_t)KC * 4 * 8192 + (size_t)TCS_STAGES * 4 * TCS_TILE + 1024 + 512 + 2 * 8192;
+            static bool attr_done = false;
+            if (!attr_done) { BCUDA(cudaFuncSetAttribute(k_big_scores_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_optin)); attr_done = true; }
+            const unsigned long long tiles = (b->S_local + 127) / 128;
+            const unsigned gx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(tiles, (unsigned long long)b->sm_count));
+            k_big_scores_tc<<<dim3(gx, qblocks), TCS_WARPS * 32, smem, st>>>(tp);
+            count_launch();
+            BCUDA(cudaPeekAtLastError());
+            rc = QMANN_OK;
+        }
+        else if (b->fast[h] && b->mma_ok && Q >= 4) {
             const unsigned qblocks = (Q + MMA_QB - 1) / MMA_QB;
             const unsigned frag_vec = (d / 32) * 8 * 2 * 32;
             k_big_prep_bfrag<<<std::min(256u, (qblocks * frag_vec + 255) / 256), 256, 0, st>>>(b->ub8, Q, d, b->bfrag);
