@@ -611,16 +611,17 @@ __global__ void __launch_bounds__(256) k_big_prep_bfrag(const signed char *__res
 //
 // One persistent CTA per SM and query block of 64.  Per tile of 128 slots and 128-byte K chunk:
 //   producer thread : TMA box (128 bytes x 128 rows, 128-byte swizzle) of Y -> stage;  Y itself is plane 0 of the A operand
-//   12 builder warps: the three indicator planes of every 16-byte chunk, written at the SAME offset of three more tiles (the map is
+//   8 builder warps : the three indicator planes of every 16-byte chunk, written at the SAME offset of three more tiles (the map is
 //                     elementwise, so the swizzled layout carries over), then fence.proxy.async so that the tensor core sees them
 //   MMA thread      : 4 planes x 4 K steps of tcgen05.mma M128 N64 K32 into ONE accumulator tile (the query planes of a = 1..3
 //                     are stored negated); tcgen05.commit frees the stage, and after the last chunk hands the tile to the epilogue
 //   8 epilogue warps: (two per quadrant of tensor memory, 32 queries each) tcgen05.ld, (acc >> 2) clamped -> score bin per
 //                     (query, slot); entries whose products may saturate are recomputed product by product (same rule as the
 //                     other fast scorers)
-// Two stages, two accumulator tiles (2 x 64 TMEM columns).  The memory is streamed once per block of 64 queries.
+// The Y tiles sit in a ring of three (the TMA runs three deep: a 16 KB box takes ~2 300 cycles to arrive), the plane tiles in a ring
+// of two, two accumulator tiles (2 x 64 TMEM columns).  The memory is streamed once per block of 64 queries.
 // -------------------------------------------------------------------------------------------------
-constexpr unsigned TCS_QB = 64, TCS_STAGES = 2, TCS_TILE = 128 * 128, TCS_BUILDERS = 12;
+constexpr unsigned TCS_QB = 64, TCS_NY = 3, TCS_NP = 2, TCS_TILE = 128 * 128, TCS_BUILDERS = 8;
 constexpr unsigned TCS_EPI = 8;                       // epilogue warps: two per TMEM quadrant, 32 accumulator columns each
 // warp roles: the issue arbiter of an SM sub-partition favours the highest warp ids, so the epilogue (the critical path once the tensor
 // core is fed) gets them: builders first, then the producer, the MMA issuer, and the eight epilogue warps
@@ -680,10 +681,10 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __gri
     const unsigned KC = p.d / 128;                                     // K chunks per tile
     const unsigned sraw = smem_u32(sm), sbase = (sraw + 1023u) & ~1023u;
     unsigned char *gbase = sm + (sbase - sraw);
-    // layout: [B planes: KC x 4 x 8 KB][stages: 2 x 4 planes x 16 KB][control, 512 B][two score-bin tiles of 64 x 128 bytes]
-    const unsigned bsm = sbase, stg = bsm + KC * 4u * 8192u, cb = stg + TCS_STAGES * 4u * TCS_TILE;
+    // layout: [B planes: KC x 4 x 8 KB][Y ring: 3 x 16 KB][plane ring: 2 x 3 x 16 KB][control, 512 B][two score-bin tiles of 64 x 128 bytes]
+    const unsigned bsm = sbase, yrg = bsm + KC * 4u * 8192u, prg = yrg + TCS_NY * TCS_TILE, cb = prg + TCS_NP * 3u * TCS_TILE;
     unsigned char *cbg = gbase + (cb - sbase);
-    const unsigned bar_full = cb, bar_built = cb + 16, bar_empty = cb + 32, bar_dfull = cb + 48, bar_dfree = cb + 64, tmem_slot = cb + 80;
+    const unsigned bar_yfull = cb, bar_yfree = cb + 24, bar_built = cb + 48, bar_pfree = cb + 64, bar_dfull = cb + 80, bar_dfree = cb + 96, tmem_slot = cb + 112;
     unsigned *umax_s = reinterpret_cast<unsigned *>(cbg + 128);
     const unsigned q0 = blockIdx.y * TCS_QB;
     {
@@ -693,10 +694,9 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __gri
         for (unsigned i = threadIdx.x; i < TCS_QB; i += blockDim.x) umax_s[i] = (q0 + i < p.Q) ? p.umax[q0 + i] : 0u;
     }
     if (threadIdx.x == 0) {
-        for (unsigned s = 0; s < TCS_STAGES; s++) {
-            mbar_init(bar_full + 8 * s, 1); mbar_init(bar_built + 8 * s, TCS_BUILDERS); mbar_init(bar_empty + 8 * s, 1);
-            mbar_init(bar_dfull + 8 * s, 1); mbar_init(bar_dfree + 8 * s, TCS_EPI);
-        }
+        for (unsigned s = 0; s < TCS_NY; s++) { mbar_init(bar_yfull + 8 * s, 1); mbar_init(bar_yfree + 8 * s, 1); }
+        for (unsigned s = 0; s < TCS_NP; s++) { mbar_init(bar_built + 8 * s, TCS_BUILDERS); mbar_init(bar_pfree + 8 * s, 1); }
+        for (unsigned s = 0; s < 2; s++) { mbar_init(bar_dfull + 8 * s, 1); mbar_init(bar_dfree + 8 * s, TCS_EPI); }
         mbar_fence_init();
         tma_prefetch_desc(&p.tmY);
     }
@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const unsigned tmem = *reinterpret_cast<const unsigned *>(cbg + 80);
+    const unsigned tmem = *reinterpret_cast<const unsigned *>(cbg + 112);
     const unsigned long long n_tiles = (p.S_local + 127ull) / 128ull;
 
     if (warp == TCS_W_PROD) {
@@ -714,12 +714,12 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __gri
             SCK_DECL
             for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (unsigned kc = 0; kc < KC; kc++, it++) {
-                    const unsigned s = it % TCS_STAGES, ph = (it / TCS_STAGES) & 1u;
+                    const unsigned s = it % TCS_NY, ph = (it / TCS_NY) & 1u;
                     SCK(1);
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    mbar_wait(bar_yfree + 8 * s, ph ^ 1u);
                     SCK(0);
-                    mbar_expect_tx(bar_full + 8 * s, TCS_TILE);
-                    tma_load_2d(stg + s * 4u * TCS_TILE, &p.tmY, (int)(128u * kc), (int)(tile * 128ull), bar_full + 8 * s);
+                    mbar_expect_tx(bar_yfull + 8 * s, TCS_TILE);
+                    tma_load_2d(yrg + s * TCS_TILE, &p.tmY, (int)(128u * kc), (int)(tile * 128ull), bar_yfull + 8 * s);
                 }
             SCK(1); SCK_FLUSH(0);
         }
@@ -727,14 +727,9 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __gri
         if (lane == 0) {
             const unsigned idesc = umma_idesc_i8(128, TCS_QB);
             unsigned it = 0, tc = 0;
-            // descriptors of the 2 x 4 A tiles and of the B tiles are formed once; an MMA then only steps the start-address field
-            // (+2 per 32 bytes of K)
-            unsigned long long adesc[TCS_STAGES][4];
-#pragma unroll
-            for (unsigned s_ = 0; s_ < TCS_STAGES; s_++)
-#pragma unroll
-                for (unsigned pl = 0; pl < 4; pl++) adesc[s_][pl] = umma_desc_sw128(stg + (s_ * 4u + pl) * TCS_TILE);
-            const unsigned long long bdesc0 = umma_desc_sw128(bsm);
+            // descriptors of the A tiles (Y ring = plane 0, plane ring = planes 1..3) and of the B tiles are formed once; an MMA then
+            // only steps the start-address field (+2 per 32 bytes of K)
+            const unsigned long long ydesc0 = umma_desc_sw128(yrg), pdesc0 = umma_desc_sw128(prg), bdesc0 = umma_desc_sw128(bsm);
             SCK_DECL
             for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tc++) {
                 const unsigned buf = tc & 1u;
@@ -743,19 +738,21 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __gri
                 SCK(0);
                 tc_fence_after();
                 for (unsigned kc = 0; kc < KC; kc++, it++) {
-                    const unsigned s = it % TCS_STAGES, ph = (it / TCS_STAGES) & 1u;
+                    const unsigned ys = it % TCS_NY, ps = it % TCS_NP, php = (it / TCS_NP) & 1u;
                     SCK(2);
-                    mbar_wait(bar_built + 8 * s, ph);
+                    mbar_wait(bar_built + 8 * ps, php);                     // implies the Y tile has arrived (the builders read it)
                     SCK(1);
                     tc_fence_after();
 #pragma unroll
                     for (unsigned pl = 0; pl < 4; pl++) {
-                        const unsigned long long ad = (s == 0) ? adesc[0][pl] : adesc[1][pl];
+                        const unsigned long long ad = pl == 0 ? ydesc0 + (unsigned long long)(ys * (TCS_TILE >> 4))
+                                                              : pdesc0 + (unsigned long long)((ps * 3u + pl - 1u) * (TCS_TILE >> 4));
                         const unsigned long long bd = bdesc0 + (unsigned long long)((kc * 4u + pl) * (8192u >> 4));
 #pragma unroll
                         for (unsigned j = 0; j < 4; j++) umma_i8(tmem + buf * TCS_QB, ad + 2ull * j, bd + 2ull * j, idesc, (kc | pl | j) ? 1u : 0u);
                     }
-                    umma_commit(bar_empty + 8 * s);
+                    umma_commit(bar_yfree + 8 * ys);
+                    umma_commit(bar_pfree + 8 * ps);
                 }
                 umma_commit(bar_dfull + 8 * buf);
             }
@@ -767,11 +764,13 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __gri
         SCK_DECL
         for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
             for (unsigned kc = 0; kc < KC; kc++, it++) {
-                const unsigned s = it % TCS_STAGES, ph = (it / TCS_STAGES) & 1u;
+                const unsigned ys = it % TCS_NY, phy = (it / TCS_NY) & 1u, ps = it % TCS_NP, php = (it / TCS_NP) & 1u;
                 SCK(1);
-                mbar_wait(bar_full + 8 * s, ph);
+                mbar_wait(bar_pfree + 8 * ps, php ^ 1u);                   // the MMAs that read this plane buffer have completed
+                mbar_wait(bar_yfull + 8 * ys, phy);
                 SCK(0);
-                unsigned char *y0 = gbase + (stg - sbase) + (size_t)s * 4u * TCS_TILE;
+                const unsigned char *y0 = gbase + (yrg - sbase) + (size_t)ys * TCS_TILE;
+                unsigned char *p0 = gbase + (prg - sbase) + (size_t)ps * 3u * TCS_TILE;
 #pragma unroll
                 for (unsigned i = 0; i < (TCS_TILE / 16u + TCS_BUILDERS * 32u - 1u) / (TCS_BUILDERS * 32u); i++) {
                     const unsigned off = 16u * (bt + i * TCS_BUILDERS * 32u);
@@ -782,13 +781,13 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __gri
                     indicator_planes(y.y, i1.y, i2.y, i3.y);
                     indicator_planes(y.z, i1.z, i2.z, i3.z);
                     indicator_planes(y.w, i1.w, i2.w, i3.w);
-                    *reinterpret_cast<uint4 *>(y0 + TCS_TILE + off) = i1;
-                    *reinterpret_cast<uint4 *>(y0 + 2u * TCS_TILE + off) = i2;
-                    *reinterpret_cast<uint4 *>(y0 + 3u * TCS_TILE + off) = i3;
+                    *reinterpret_cast<uint4 *>(p0 + off) = i1;
+                    *reinterpret_cast<uint4 *>(p0 + TCS_TILE + off) = i2;
+                    *reinterpret_cast<uint4 *>(p0 + 2u * TCS_TILE + off) = i3;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_built + 8 * s);
+                if (lane == 0) mbar_arrive(bar_built + 8 * ps);
             }
         SCK(1);
         if (warp == TCS_W_BUILD) SCK_FLUSH(2);
@@ -1549,7 +1548,7 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
     {
         // tcgen05 scorer: every fast hop's Y as a TMA tensor, the B planes' image; QMANN_BIGMEM_TC=0 keeps the mma.sync kernel
         const char *env_tc = getenv("QMANN_BIGMEM_TC");
-        const size_t need = (size_t)(c.d / 128) * 4 * 8192 + (size_t)TCS_STAGES * 4 * TCS_TILE + 1024 + 512 + 2 * 8192;
+        const size_t need = (size_t)(c.d / 128) * 4 * 8192 + (size_t)(TCS_NY + 3 * TCS_NP) * TCS_TILE + 1024 + 512 + 2 * 8192;
         bool ok = b->mma_ok && c.d % 128 == 0 && c.d >= 128 && need <= (size_t)b->smem_optin && !(env_tc && atoi(env_tc) == 0);
         for (unsigned h = 0; h < c.H && ok; h++)
             if (b->fast[h]) ok = tmap_bytes_rows(&b->tmY[h], b->Y[h], S_local, c.d);
@@ -1618,7 +1617,7 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
             { unsigned long long *dp = nullptr; BCUDA(cudaHostGetDevicePointer((void **)&dp, clk_host, 0)); tp.clk = dp; }
             g_tcs_clk = clk_host;
 #endif
-            const size_t smem = (size_t)KC * 4 * 8192 + (size_t)TCS_STAGES * 4 * TCS_TILE + 1024 + 512 + 2 * 8192;
+            const size_t smem = (size_t)KC * 4 * 8192 + (size_t)(TCS_NY + 3 * TCS_NP) * TCS_TILE + 1024 + 512 + 2 * 8192;
             static bool attr_done = false;
             if (!attr_done) { BCUDA(cudaFuncSetAttribute(k_big_scores_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_optin)); attr_done = true; }
             const unsigned long long tiles = (b->S_local + 127) / 128;
