@@ -312,6 +312,13 @@ int  qmann_bigmem_hop_update(qmann_bigmem *b, uint32_t h, const int32_t *dev_par
 int  qmann_bigmem_state(qmann_bigmem *b, int8_t *dev_u, int32_t *frac_bits, void *stream);
 /* Answer projection (fp32, index order), softmax, argmax_last.  dev_z/dev_h: optional fp32 [Q][V]. */
 int  qmann_bigmem_finish(qmann_bigmem *b, uint32_t *dev_pred, float *dev_z, float *dev_h, void *stream);
+/* The whole forward of a query batch in ONE call (SURVEY 8b "qmann_forward_sharded"): begin, then per hop scores -> all-reduce(SUM, u32
+ * histograms) -> read -> all-reduce(SUM, i32 partial reads) -> update, then the answer projection.  nccl_comm: the caller's ncclComm_t
+ * spanning the shards (one rank per GPU, created by the host with ncclCommInitRank), or NULL for a single shard; ncclAllReduce is resolved
+ * at run time from the libnccl.so.2 of the process (the library does not link NCCL).  On a non-default stream the sequence is captured once
+ * per (u0, Q, pred, comm) into a CUDA graph and replayed (QMANN_BIGMEM_GRAPH=0 disables that).  dev_pred may be NULL (no answer layer);
+ * the controller state is available through qmann_bigmem_state() afterwards.  Collective: every rank must make the same calls. */
+int  qmann_bigmem_forward_sharded(qmann_bigmem *b, void *nccl_comm, const int8_t *dev_u0, uint32_t Q, uint32_t *dev_pred, void *stream);
 /* Optional CUDA-event timing of the dominant kernel (k_big_scores, one launch per hop).  _read folds the pending
  * event pairs (at most one forward's worth: call it after every forward while enabled), synchronising on them. */
 int  qmann_bigmem_profile_enable(qmann_bigmem *b, int enable);

@@ -32,6 +32,8 @@
 #include "qmann_tc.cuh"
 #include "../../include/qmann_abi.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -1335,6 +1337,14 @@ struct qmann_bigmem {
     unsigned *umax;                  // [Q_max] max |Q_bin(u)|
     uint4 *bfrag;                    // k_big_scores_mma query planes, fragment order
     bool mma_ok;
+    // qmann_bigmem_forward_sharded: exchange buffers and the captured graph of one whole forward
+    uint32_t *xhist;
+    int32_t *xpartial;
+    cudaGraphExec_t gexec;
+    const void *g_u0, *g_pred, *g_comm;
+    unsigned g_Q;
+    const void *warm_comm;
+    bool warm;
     // k_big_scores_tc (tcgen05): query planes as the B operand's shared-memory image, one tensor map of Y per hop
     uint4 *bplanes;
     bool tc_ok;
@@ -1565,6 +1575,8 @@ void qmann_bigmem_destroy(qmann_bigmem *b)
     if (!b) return;
     cudaFree(b->u_a); cudaFree(b->u_b); cudaFree(b->ub); cudaFree(b->av); cudaFree(b->sv); cudaFree(b->bins);
     cudaFree(b->ub8); cudaFree(b->umax); cudaFree(b->bfrag); cudaFree(b->bplanes);
+    cudaFree(b->xhist); cudaFree(b->xpartial);
+    if (b->gexec) cudaGraphExecDestroy(b->gexec);
     for (int h = 0; h < MAXH; h++) { cudaFree(b->Y_own[h]); cudaFree(b->rowmax[h]); }
     cudaFree(b->pq); cudaFree(b->thr); cudaFree(b->nsel); cudaFree(b->zbuf);
     for (int h = 0; h < MAXH; h++) cudaFree(b->dev_H[h]);
@@ -1758,6 +1770,75 @@ int qmann_bigmem_finish(qmann_bigmem *b, uint32_t *dev_pred, float *dev_z, float
     k_big_answer<<<(b->Q * 32 + 127) / 128, 128, (size_t)4 * b->cfg.d * 4, st>>>(b->dev_W, b->u_a, b->fu, b->Q, b->cfg.V, b->cfg.d, z, dev_pred, dev_h);
     count_launch();
     BCUDA(cudaPeekAtLastError());
+    return QMANN_OK;
+}
+
+// ---- the whole slot-sharded forward as ONE call: phases + the two exchanges per hop on the caller's NCCL communicator ----
+namespace {
+// ncclAllReduce resolved at run time from the NCCL the process already uses (the library itself does not link NCCL):
+//   ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+nccl_allreduce_fn nccl_allreduce()
+{
+    static nccl_allreduce_fn fn = []() -> nccl_allreduce_fn {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        return h ? (nccl_allreduce_fn)dlsym(h, "ncclAllReduce") : nullptr;
+    }();
+    return fn;
+}
+constexpr int NCCL_INT32 = 2, NCCL_UINT32 = 3, NCCL_SUM = 0;      // nccl.h: ncclInt32, ncclUint32, ncclSum
+
+int forward_phases(qmann_bigmem *b, void *comm, const int8_t *dev_u0, uint32_t Q, uint32_t *dev_pred, cudaStream_t st)
+{
+    nccl_allreduce_fn ar = comm ? nccl_allreduce() : nullptr;
+    if (comm && !ar) return bfail(QMANN_E_ARG, "libnccl.so.2 not found: cannot run the exchanges of a sharded forward");
+    int rc;
+    if ((rc = qmann_bigmem_begin(b, dev_u0, Q, st))) return rc;
+    for (uint32_t h = 0; h < b->cfg.H; h++) {
+        if ((rc = qmann_bigmem_hop_scores(b, h, b->xhist, st))) return rc;
+        if (ar && ar(b->xhist, b->xhist, (size_t)Q * b->NB, NCCL_UINT32, NCCL_SUM, comm, st) != 0) return bfail(QMANN_E_CUDA, "ncclAllReduce (score histograms) failed");
+        if ((rc = qmann_bigmem_hop_read(b, h, b->xhist, b->xpartial, nullptr, st))) return rc;
+        if (ar && ar(b->xpartial, b->xpartial, (size_t)Q * b->cfg.d, NCCL_INT32, NCCL_SUM, comm, st) != 0) return bfail(QMANN_E_CUDA, "ncclAllReduce (partial reads) failed");
+        if ((rc = qmann_bigmem_hop_update(b, h, b->xpartial, nullptr, nullptr, st))) return rc;
+    }
+    if (dev_pred && b->dev_W && b->cfg.V) return qmann_bigmem_finish(b, dev_pred, nullptr, nullptr, st);
+    return QMANN_OK;
+}
+}  // namespace
+
+int qmann_bigmem_forward_sharded(qmann_bigmem *b, void *nccl_comm, const int8_t *dev_u0, uint32_t Q, uint32_t *dev_pred, void *stream)
+{
+    if (!b || !dev_u0) return bfail(QMANN_E_ARG, "null argument");
+    if (Q == 0 || Q > b->Q_max) return bfail(QMANN_E_ARG, "Q must be in 1..Q_max");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!b->xhist) BCUDA(cudaMalloc((void **)&b->xhist, (size_t)b->Q_max * b->NB * 4));
+    if (!b->xpartial) BCUDA(cudaMalloc((void **)&b->xpartial, (size_t)b->Q_max * b->cfg.d * 4));
+    const char *env_graph = getenv("QMANN_BIGMEM_GRAPH");
+    const bool use_graph = !(env_graph && atoi(env_graph) == 0) && !b->profile && st != nullptr;      // the legacy default stream cannot be captured
+    if (!use_graph) return forward_phases(b, nccl_comm, dev_u0, Q, dev_pred, st);
+    if (!b->warm || b->warm_comm != nccl_comm) {
+        // the first forward on a communicator runs un-captured: NCCL sets its channels up inside the first collective (allocations,
+        // synchronisation), which a stream capture must not see; it is captured from the second call on
+        b->warm = true; b->warm_comm = nccl_comm;
+        return forward_phases(b, nccl_comm, dev_u0, Q, dev_pred, st);
+    }
+    if (!b->gexec || b->g_u0 != dev_u0 || b->g_pred != dev_pred || b->g_comm != nccl_comm || b->g_Q != Q) {
+        // (re)capture: about twenty launches, two memsets and six collectives become one graph launch per forward
+        if (b->gexec) { cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        BCUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        const int rc = forward_phases(b, nccl_comm, dev_u0, Q, dev_pred, st);
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess || !graph) return bfail(QMANN_E_CUDA, std::string("stream capture of the forward failed: ") + cudaGetErrorString(ce));
+        const cudaError_t ie = cudaGraphInstantiate(&b->gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { b->gexec = nullptr; return bfail(QMANN_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+        b->g_u0 = dev_u0; b->g_pred = dev_pred; b->g_comm = nccl_comm; b->g_Q = Q;
+    }
+    BCUDA(cudaGraphLaunch(b->gexec, st));
     return QMANN_OK;
 }
 

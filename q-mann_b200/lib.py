@@ -106,6 +106,8 @@ def lib() -> C.CDLL:
     L.qmann_bigmem_destroy.argtypes = [C.c_void_p]
     L.qmann_bigmem_num_bins.restype = _U32
     L.qmann_bigmem_num_bins.argtypes = [C.c_void_p]
+    L.qmann_bigmem_forward_sharded.restype = C.c_int
+    L.qmann_bigmem_forward_sharded.argtypes = [C.c_void_p, C.c_void_p, _FP, _U32, _FP, C.c_void_p]
     L.qmann_bigmem_begin.restype = C.c_int
     L.qmann_bigmem_begin.argtypes = [C.c_void_p, _FP, _U32, C.c_void_p]
     L.qmann_bigmem_hop_scores.restype = C.c_int
@@ -381,6 +383,38 @@ def slot_shard(S_total: int, world: int, rank: int):
     return lo, hi - lo
 
 
+class NcclComm:
+    """A NCCL communicator over the ranks of the default torch.distributed group, for qmann_bigmem_forward_sharded (a C host
+    would call ncclGetUniqueId / ncclCommInitRank itself; torch does not expose the ncclComm_t of its process groups).
+    Rank 0 makes the unique id, the group broadcasts it, every rank initialises its communicator on the current device."""
+
+    class _Uid(C.Structure):
+        _fields_ = [("internal", C.c_char * 128)]
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.nccl = C.CDLL("libnccl.so.2")               # the library the process (torch) already uses
+        self.nccl.ncclGetUniqueId.argtypes = [C.POINTER(NcclComm._Uid)]
+        self.nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, NcclComm._Uid, C.c_int]
+        self.nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+        uid = NcclComm._Uid()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if rank == 0 and self.nccl.ncclGetUniqueId(C.byref(uid)) != 0:
+            raise QmannError("ncclGetUniqueId failed")
+        t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).cuda()
+        dist.broadcast(t, src=0)
+        C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+        self.comm = C.c_void_p()
+        if self.nccl.ncclCommInitRank(C.byref(self.comm), world, uid, rank) != 0:
+            raise QmannError("ncclCommInitRank failed")
+
+    def close(self):
+        if self.comm:
+            self.nccl.ncclCommDestroy(self.comm)
+            self.comm = C.c_void_p()
+
+
 class BigMemory:
     """One very large pre-embedded memory, this rank's slot shard resident in HBM (include/qmann_abi.h part 3).
 
@@ -444,6 +478,16 @@ class BigMemory:
         if self.group is not None and self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def forward_sharded(self, u0, comm: Optional["NcclComm"] = None):
+        """The whole forward in one C call (qmann_bigmem_forward_sharded): the exchanges run on `comm` (None: a single shard);
+        on a non-default current stream the sequence is captured into a CUDA graph once and replayed.  Returns the predictions."""
+        torch = self.torch
+        Q = int(u0.shape[0])
+        assert u0.dtype == torch.int8 and u0.is_cuda and u0.is_contiguous() and Q <= self.Q_max
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _bcheck(lib().qmann_bigmem_forward_sharded(self._h, comm.comm if comm is not None else None, u0.data_ptr(), Q, self.pred.data_ptr(), st))
+        return self.pred[:Q]
 
     def forward(self, u0, debug: bool = False, answer: bool = True):
         """u0: int8 [Q][d] device tensor (codes in the hop-0 weight format).  Asynchronous on the current stream.

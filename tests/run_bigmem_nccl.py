@@ -25,6 +25,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     pkg = ge.import_package()
     ok = True
+    comm = pkg.lib.NcclComm()                          # our own communicator for the one-call C entry
+    side = torch.cuda.Stream()
     for mode in (2, 3):
         cfg = pkg.synth.ModelConfig(V=40, d=64, S_max=64, V_dict=20, mode=mode, iwl=5 if mode == 2 else 3)
         w = pkg.synth.make_weights(cfg, 6, sigma=0.5)
@@ -35,6 +37,17 @@ def main():
         u0d = torch.from_numpy(u0).cuda()
         out = mem.forward(u0d, debug=True)
         torch.cuda.synchronize()
+        # qmann_bigmem_forward_sharded: phases + ncclAllReduce inside the library, captured into a CUDA graph on a side stream
+        pred_phase = out["pred"].clone()
+        for rep in range(3):                               # capture, then two replays
+            with torch.cuda.stream(side):
+                pred_one = mem.forward_sharded(u0d, comm).clone()
+            side.synchronize()
+            same = torch.equal(pred_one, pred_phase)
+            ok = ok and same
+            if not same:
+                print(f"mode {mode}: one-call sharded forward (rep {rep}) differs from the phase API on rank {rank}", flush=True)
+        out["pred"] = pred_phase
         if rank == 0:
             full = pkg.lib.BigMemory(cfg, w, M8, C8, S, 0, Q_max=16, device=f"cuda:{local}")
             ref = full.forward(u0d, debug=True)
@@ -49,6 +62,7 @@ def main():
     if rank == 0:
         print("BIGMEM_NCCL_OK" if int(flag.item()) == 1 else "BIGMEM_NCCL_FAIL", flush=True)
     dist.barrier()
+    comm.close()
     dist.destroy_process_group()
     return 0 if int(flag.item()) == 1 else 1
 

@@ -192,3 +192,32 @@ def test_bigmem_nccl_two_ranks(qmann):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "BIGMEM_NCCL_OK" in r.stdout
+
+
+@pytest.mark.parametrize("mode,d,Q", [(2, 256, 70), (2, 64, 3), (3, 64, 5)])
+def test_bigmem_one_call_forward_equals_phase_api(mode, d, Q, qmann, synth):
+    """qmann_bigmem_forward_sharded on a single shard (no communicator): the whole forward as one C call, captured into a CUDA graph
+    on a side stream and replayed, and un-captured on the default stream -- same predictions and controller state as the phase API."""
+    import torch
+    cfg = synth.ModelConfig(V=40, d=d, S_max=64, V_dict=20, mode=mode, iwl=5 if mode == 2 else 3)
+    w = synth.make_weights(cfg, 8, sigma=0.5)
+    M8, C8, u0 = _random_memory(cfg, 3001, Q, 1234 + d, sigma=0.6 if mode == 2 else 0.3, plant_scale=3.0 if mode == 2 else 1.0)
+    mem = qmann.lib.BigMemory(cfg, w, M8, C8, M8.shape[1], 0, Q_max=Q)
+    u0d = torch.from_numpy(u0).cuda()
+    ref = mem.forward(u0d)
+    torch.cuda.synchronize()
+    pred_ref, u_ref = ref["pred"].clone(), ref["u_final"].clone()
+    side = torch.cuda.Stream()
+    u0b = u0d.clone()
+    for rep in range(3):                       # capture + two replays; then another input buffer forces a re-capture
+        with torch.cuda.stream(side):
+            got = mem.forward_sharded(u0d if rep < 2 else u0b).clone()
+        side.synchronize()
+        assert torch.equal(got, pred_ref), f"graph path, call {rep}"
+    got = mem.forward_sharded(u0d).clone()     # legacy default stream: not captured
+    torch.cuda.synchronize()
+    assert torch.equal(got, pred_ref)
+    uu = torch.zeros_like(u_ref)
+    qmann.lib._bcheck(qmann.lib.lib().qmann_bigmem_state(mem._h, uu.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    assert torch.equal(uu, u_ref)
