@@ -400,19 +400,24 @@ class NcclComm:
         self.nccl.ncclCommDestroy.argtypes = [C.c_void_p]
         uid = NcclComm._Uid()
         rank, world = dist.get_rank(), dist.get_world_size()
+        dbg = (lambda *a: print(f"[NcclComm rank {rank}]", *a, flush=True)) if os.environ.get("QMANN_NCCL_DEBUG") else (lambda *a: None)
         if rank == 0 and self.nccl.ncclGetUniqueId(C.byref(uid)) != 0:
             raise QmannError("ncclGetUniqueId failed")
+        dbg("unique id made")
         t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).cuda()
         dist.broadcast(t, src=0)
         C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+        dbg("unique id broadcast; ncclCommInitRank")
         self.comm = C.c_void_p()
         if self.nccl.ncclCommInitRank(C.byref(self.comm), world, uid, rank) != 0:
             raise QmannError("ncclCommInitRank failed")
 
-    def close(self):
-        if self.comm:
+    def close(self, destroy: bool = False):
+        """Forget the communicator.  ncclCommDestroy is only called on request: it blocks while CUDA graphs that captured collectives
+        of this communicator are alive (destroy the BigMemory objects first); otherwise process exit reclaims it."""
+        if self.comm and destroy:
             self.nccl.ncclCommDestroy(self.comm)
-            self.comm = C.c_void_p()
+        self.comm = C.c_void_p()
 
 
 class BigMemory:

@@ -25,7 +25,10 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     pkg = ge.import_package()
     ok = True
+    dbg = lambda *a: print(f"[rank {rank}]", *a, flush=True) if os.environ.get("QMANN_NCCL_DEBUG") else None
+    dbg("creating NcclComm")
     comm = pkg.lib.NcclComm()                          # our own communicator for the one-call C entry
+    dbg("NcclComm ready")
     side = torch.cuda.Stream()
     for mode in (2, 3):
         cfg = pkg.synth.ModelConfig(V=40, d=64, S_max=64, V_dict=20, mode=mode, iwl=5 if mode == 2 else 3)
@@ -39,10 +42,12 @@ def main():
         torch.cuda.synchronize()
         # qmann_bigmem_forward_sharded: phases + ncclAllReduce inside the library, captured into a CUDA graph on a side stream
         pred_phase = out["pred"].clone()
-        for rep in range(3):                               # capture, then two replays
+        for rep in range(3):                               # un-captured first call, capture, replay
+            dbg(f"mode {mode} forward_sharded rep {rep}")
             with torch.cuda.stream(side):
                 pred_one = mem.forward_sharded(u0d, comm).clone()
             side.synchronize()
+            dbg(f"mode {mode} forward_sharded rep {rep} done")
             same = torch.equal(pred_one, pred_phase)
             ok = ok and same
             if not same:
