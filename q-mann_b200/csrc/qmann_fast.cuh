@@ -301,6 +301,35 @@ __device__ __forceinline__ int swar_score(const unsigned (&acc4)[4], unsigned Bw
     return D - (int)__dp4a(cs, SW_1, 0u) + 48;
 }
 
+// DP == 64 (LPR == 4): lane l owns dims 2l, 2l+1 of every d-vector.  (a0, a1) and (b0, b1) += the table codes of those dims over the
+// entries [ea, ea + 2 na) and [eb, eb + 2 nb) of the warp's entry list (shared byte addresses; 16-bit byte offsets column * DP): one
+// coalesced 64-byte table row per entry and warp, two rows' gathers interleaved so that their L2 round trips overlap.
+__device__ __forceinline__ unsigned ldg_na_u16(const void *ptr)
+{
+    unsigned short r;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(ptr));
+    return (unsigned)r;
+}
+__device__ __forceinline__ void gather2x2(unsigned ea, unsigned na, unsigned eb, unsigned nb, const unsigned char *__restrict__ tab, unsigned lane, int &a0, int &a1,
+                                          int &b0, int &b1)
+{
+    const unsigned char *t16 = tab + 2u * lane;
+    const unsigned n = max(na, nb);
+#pragma unroll 4
+    for (unsigned e = 0; e < n; e++) {
+        unsigned short offa = 0, offb = 0;
+        if (e < na) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(offa) : "r"(ea + 2u * e));
+        if (e < nb) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(offb) : "r"(eb + 2u * e));
+        unsigned wa = 0, wb = 0;
+        if (e < na) wa = ldg_na_u16(t16 + offa);
+        if (e < nb) wb = ldg_na_u16(t16 + offb);
+        a0 += (int)(signed char)(wa & 0xFFu);
+        a1 += (int)(signed char)(wa >> 8);
+        b0 += (int)(signed char)(wb & 0xFFu);
+        b1 += (int)(signed char)(wb >> 8);
+    }
+}
+
 // Tier tag written to dbg.dev_path / counted in p.path_count
 constexpr unsigned PATH_PACKED = 1u, PATH_UNPACKED = 2u, PATH_GENERAL = 3u;
 
@@ -833,125 +862,176 @@ __global__ void __launch_bounds__(MAXT, 1) k_story(const __grid_constant__ FwdPa
             }
             __syncwarp();
 
+            if (LPR == 4 && (!p.lin_map || p.lut)) {
+                // ---- DP == 64: lane l owns dims 2l, 2l+1 of o, g and u.  Weighted read over the selected slots (layer_cuda.cu:547-579):
+                //      their C_h rows are gathered with one coalesced 64-byte table row per entry, two slots at a time ----
+                const unsigned c0 = 2u * lane;
+                int o0 = 0, o1 = 0;
+                const unsigned char *ctab = p.img + p.offC[h];
+#pragma unroll 1
+                for (unsigned k = 0; k < nnz; k += 2) {
+                    const bool two = (k + 1 < nnz);
+                    const unsigned ra = (unsigned)sc[k] + 1u, rb = two ? (unsigned)sc[k + 1] + 1u : ra;      // record rows (0 = question)
+                    const unsigned ba = rend_s[ra - 1], bb = rend_s[rb - 1];
+                    const unsigned na = rend_s[ra] - ba, nb = two ? rend_s[rb] - bb : 0u;
+                    int a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+                    gather2x2(smem_u32(ws) + 2u * ba, na, smem_u32(ws) + 2u * bb, nb, ctab, lane, a0, a1, b0, b1);
+                    const int pa = (int)pq[k], pb = two ? (int)pq[k + 1] : 0;
+                    o0 += qi_mul(pa, qi_requant(qi_clamp(a0, lw), fw, lf, ff), lf, ff) + qi_mul(pb, qi_requant(qi_clamp(b0, lw), fw, lf, ff), lf, ff);
+                    o1 += qi_mul(pa, qi_requant(qi_clamp(a1, lw), fw, lf, ff), lf, ff) + qi_mul(pb, qi_requant(qi_clamp(b1, lw), fw, lf, ff), lf, ff);
+                }
+                o0 = qi_clamp(o0, lf); o1 = qi_clamp(o1, lf);
+                if (DUMP && p.dbg.dev_o) {
+                    if (c0 < d) p.dbg.dev_o[((size_t)h * p.n_total + story) * d + c0] = (float)o0 / (float)(1 << ff);
+                    if (c0 + 1 < d) p.dbg.dev_o[((size_t)h * p.n_total + story) * d + c0 + 1] = (float)o1 / (float)(1 << ff);
+                }
+                // ---- linear map (MemN2N.c:873, layer_cuda.cu:49-68): g[i] = Q_w(sum_j T[j][Q_bin(u[j])][i]), one byte of a product-table
+                //      row per (j, i); update (MemN2N.c:889, layer_cuda.cu:1535) ----
+                int g0, g1, gfrac;
+                if (p.lin_map) {
+                    g0 = 0; g1 = 0;
+                    const unsigned short *lut16 = reinterpret_cast<const unsigned short *>(p.lut + p.offL[h]) + lane;
+#pragma unroll 25
+                    for (unsigned j = 0; j < d; j++) {
+                        const unsigned row = j * 255u + (unsigned)(ub32[j] + 127);
+                        const unsigned w_ = ldg_na_u16(lut16 + (size_t)row * (DP / 2));
+                        g0 += (int)(signed char)(w_ & 0xFFu);
+                        g1 += (int)(signed char)(w_ >> 8);
+                    }
+                    g0 = qi_clamp(g0, lw); g1 = qi_clamp(g1, lw);
+                    gfrac = fw;
+                } else {
+                    g0 = (c0 < d) ? (int)uvec[c0] : 0; g1 = (c0 + 1 < d) ? (int)uvec[c0 + 1] : 0; gfrac = fu;
+                }
+                if (DUMP && p.dbg.dev_g) {
+                    if (c0 < d) p.dbg.dev_g[((size_t)h * p.n_total + story) * d + c0] = (float)g0 / (float)(1 << gfrac);
+                    if (c0 + 1 < d) p.dbg.dev_g[((size_t)h * p.n_total + story) * d + c0 + 1] = (float)g1 / (float)(1 << gfrac);
+                }
+                const int n0 = (c0 < d) ? qi_clamp(qi_requant(g0, gfrac, lf, ff) + o0, lf) : 0;
+                const int n1 = (c0 + 1 < d) ? qi_clamp(qi_requant(g1, gfrac, lf, ff) + o1, lf) : 0;
+                __syncwarp();                                        // every lane has read uvec / ub32 of this hop
+                *reinterpret_cast<unsigned short *>(uvec + c0) = (unsigned short)((n0 & 0xFF) | ((n1 & 0xFF) << 8));
+            } else {
             // ---- weighted read over the slots with a non-zero quantised weight (layer_cuda.cu:547-579) ----
-            int oacc[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) oacc[j] = 0;
-            const unsigned char *ctab = p.img + p.offC[h] + 16u * q;
-#pragma unroll 1
-            for (unsigned k0 = 0; k0 < nnz; k0 += G) {
-                const unsigned k = k0 + g;
-                const int r = (k < nnz) ? sc[k] : -1;
-                const int pc = (k < nnz) ? (int)pq[k] : 0;
-                embed_glob<LPR>(p, wso, lane, ctab, (r >= 0) ? r + 1 : -1, acc, sel);
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int c_f = qi_requant(qi_clamp(acc[j], lw), fw, lf, ff);
-                    oacc[j] += qi_mul(pc, c_f, lf, ff);
-                }
-            }
-#pragma unroll
-            for (int o = LPR; o < 32; o <<= 1)
-#pragma unroll
-                for (int j = 0; j < 16; j++) oacc[j] += __shfl_xor_sync(0xffffffffu, oacc[j], o);
-            if (g == 0) {
-                unsigned packed[4];
-#pragma unroll
-                for (int w4 = 0; w4 < 4; w4++) {
-                    unsigned v = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; b++) v |= ((unsigned)(qi_clamp(oacc[4 * w4 + b], lf) & 0xFF)) << (8 * b);
-                    packed[w4] = v;
-                }
-                *reinterpret_cast<uint4 *>(ovec + 16 * q) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            }
-            __syncwarp();
-            if (DUMP && p.dbg.dev_o)
-                for (unsigned j = lane; j < d; j += 32) p.dbg.dev_o[((size_t)h * p.n_total + story) * d + j] = (float)ovec[j] / (float)(1 << ff);
-
-            // ---- linear map (MemN2N.c:873, layer_cuda.cu:49-68) and update (MemN2N.c:889, layer_cuda.cu:1535) ----
-            if (p.lin_map && p.lut) {
-                // g[i] = Q_w(sum_j T[j][Q_bin(u[j])][i]): every product Q_w(Q_w(Hm[i][j]) * Q_bin(u[j])) is a function of
-                // one 8-bit activation, so the d*d quantised products become a gather-and-sum of d table rows
-                int gacc[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) gacc[k] = 0;
-                const signed char *lut = p.lut + p.offL[h] + 16u * q;
-#pragma unroll 1
-                for (unsigned jb = 0; jb < d; jb += 8 * G) {
-                    // eight independent 128-bit gathers (L2-resident table) in flight per lane before the first use
-                    uint4 t[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const unsigned j = jb + (unsigned)i * G + g;
-                        t[i] = make_uint4(0u, 0u, 0u, 0u);
-                        if (j < d) t[i] = __ldg(reinterpret_cast<const uint4 *>(lut + (size_t)(j * 255u + (unsigned)(ub32[j] + 127)) * DP));
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        gacc[0] = __dp4a((int)t[i].x, sel[0], gacc[0]);   gacc[1] = __dp4a((int)t[i].x, sel[1], gacc[1]);
-                        gacc[2] = __dp4a((int)t[i].x, sel[2], gacc[2]);   gacc[3] = __dp4a((int)t[i].x, sel[3], gacc[3]);
-                        gacc[4] = __dp4a((int)t[i].y, sel[0], gacc[4]);   gacc[5] = __dp4a((int)t[i].y, sel[1], gacc[5]);
-                        gacc[6] = __dp4a((int)t[i].y, sel[2], gacc[6]);   gacc[7] = __dp4a((int)t[i].y, sel[3], gacc[7]);
-                        gacc[8] = __dp4a((int)t[i].z, sel[0], gacc[8]);   gacc[9] = __dp4a((int)t[i].z, sel[1], gacc[9]);
-                        gacc[10] = __dp4a((int)t[i].z, sel[2], gacc[10]); gacc[11] = __dp4a((int)t[i].z, sel[3], gacc[11]);
-                        gacc[12] = __dp4a((int)t[i].w, sel[0], gacc[12]); gacc[13] = __dp4a((int)t[i].w, sel[1], gacc[13]);
-                        gacc[14] = __dp4a((int)t[i].w, sel[2], gacc[14]); gacc[15] = __dp4a((int)t[i].w, sel[3], gacc[15]);
+                int oacc[16];
+    #pragma unroll
+                for (int j = 0; j < 16; j++) oacc[j] = 0;
+                const unsigned char *ctab = p.img + p.offC[h] + 16u * q;
+    #pragma unroll 1
+                for (unsigned k0 = 0; k0 < nnz; k0 += G) {
+                    const unsigned k = k0 + g;
+                    const int r = (k < nnz) ? sc[k] : -1;
+                    const int pc = (k < nnz) ? (int)pq[k] : 0;
+                    embed_glob<LPR>(p, wso, lane, ctab, (r >= 0) ? r + 1 : -1, acc, sel);
+    #pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int c_f = qi_requant(qi_clamp(acc[j], lw), fw, lf, ff);
+                        oacc[j] += qi_mul(pc, c_f, lf, ff);
                     }
                 }
-#pragma unroll
+    #pragma unroll
                 for (int o = LPR; o < 32; o <<= 1)
-#pragma unroll
-                    for (int k = 0; k < 16; k++) gacc[k] += __shfl_xor_sync(0xffffffffu, gacc[k], o);
+    #pragma unroll
+                    for (int j = 0; j < 16; j++) oacc[j] += __shfl_xor_sync(0xffffffffu, oacc[j], o);
                 if (g == 0) {
-                    const uint4 o4 = *reinterpret_cast<const uint4 *>(ovec + 16 * q);
-                    const unsigned ow[4] = {o4.x, o4.y, o4.z, o4.w};
                     unsigned packed[4];
-#pragma unroll
+    #pragma unroll
                     for (int w4 = 0; w4 < 4; w4++) {
                         unsigned v = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            const int g_w = qi_clamp(gacc[4 * w4 + b], lw);
-                            if (DUMP && p.dbg.dev_g && 16u * q + 4 * w4 + b < d)
-                                p.dbg.dev_g[((size_t)h * p.n_total + story) * d + 16u * q + 4 * w4 + b] = (float)g_w / (float)(1 << fw);
-                            const int a_f = qi_requant(g_w, fw, lf, ff);
-                            v |= ((unsigned)(qi_clamp(a_f + sbyte(ow[w4], b), lf) & 0xFF)) << (8 * b);
-                        }
+    #pragma unroll
+                        for (int b = 0; b < 4; b++) v |= ((unsigned)(qi_clamp(oacc[4 * w4 + b], lf) & 0xFF)) << (8 * b);
                         packed[w4] = v;
                     }
-                    *reinterpret_cast<uint4 *>(uvec + 16 * q) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    *reinterpret_cast<uint4 *>(ovec + 16 * q) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                 }
-            } else {
-                const int lw2 = 2 * lw;
-                const signed char *Hg = reinterpret_cast<const signed char *>(p.img + p.offH[h]);      // int8 [d][HS], L2-resident
-#pragma unroll 1
-                for (unsigned i0 = 0; i0 < d; i0 += 32) {
-                    const unsigned i = i0 + lane;
-                    int a_f = 0, g_w = 0;
-                    if (p.lin_map) {
-                        const unsigned *hrow = reinterpret_cast<const unsigned *>(Hg + (size_t)min(i, d - 1) * p.HS);
-                        int s_ = 0;
-                        const unsigned d4 = (d + 3) / 4;
-#pragma unroll 2
-                        for (unsigned j4 = 0; j4 < d4; j4++) {
-                            const unsigned hw = __ldg(hrow + j4);
-                            const int4 uu = *reinterpret_cast<const int4 *>(ub32 + 4 * j4);
-                            s_ += clamp_biased(shr0m(sbyte_prmt<0>(hw) * uu.x, fb, mb), lw, lw2);
-                            s_ += clamp_biased(shr0m(sbyte_prmt<1>(hw) * uu.y, fb, mb), lw, lw2);
-                            s_ += clamp_biased(shr0m(sbyte_prmt<2>(hw) * uu.z, fb, mb), lw, lw2);
-                            s_ += clamp_biased(shr0m(((int)hw >> 24) * uu.w, fb, mb), lw, lw2);
+                __syncwarp();
+                if (DUMP && p.dbg.dev_o)
+                    for (unsigned j = lane; j < d; j += 32) p.dbg.dev_o[((size_t)h * p.n_total + story) * d + j] = (float)ovec[j] / (float)(1 << ff);
+    
+                // ---- linear map (MemN2N.c:873, layer_cuda.cu:49-68) and update (MemN2N.c:889, layer_cuda.cu:1535) ----
+                if (p.lin_map && p.lut) {
+                    // g[i] = Q_w(sum_j T[j][Q_bin(u[j])][i]): every product Q_w(Q_w(Hm[i][j]) * Q_bin(u[j])) is a function of
+                    // one 8-bit activation, so the d*d quantised products become a gather-and-sum of d table rows
+                    int gacc[16];
+    #pragma unroll
+                    for (int k = 0; k < 16; k++) gacc[k] = 0;
+                    const signed char *lut = p.lut + p.offL[h] + 16u * q;
+    #pragma unroll 1
+                    for (unsigned jb = 0; jb < d; jb += 8 * G) {
+                        // eight independent 128-bit gathers (L2-resident table) in flight per lane before the first use
+                        uint4 t[8];
+    #pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const unsigned j = jb + (unsigned)i * G + g;
+                            t[i] = make_uint4(0u, 0u, 0u, 0u);
+                            if (j < d) t[i] = __ldg(reinterpret_cast<const uint4 *>(lut + (size_t)(j * 255u + (unsigned)(ub32[j] + 127)) * DP));
                         }
-                        g_w = qi_clamp(s_ - (int)(4u * d4) * lw, lw);
-                        a_f = qi_requant(g_w, fw, lf, ff);
-                    } else if (i < d) {
-                        g_w = (int)uvec[i];
-                        a_f = qi_requant(g_w, fu, lf, ff);
+    #pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            gacc[0] = __dp4a((int)t[i].x, sel[0], gacc[0]);   gacc[1] = __dp4a((int)t[i].x, sel[1], gacc[1]);
+                            gacc[2] = __dp4a((int)t[i].x, sel[2], gacc[2]);   gacc[3] = __dp4a((int)t[i].x, sel[3], gacc[3]);
+                            gacc[4] = __dp4a((int)t[i].y, sel[0], gacc[4]);   gacc[5] = __dp4a((int)t[i].y, sel[1], gacc[5]);
+                            gacc[6] = __dp4a((int)t[i].y, sel[2], gacc[6]);   gacc[7] = __dp4a((int)t[i].y, sel[3], gacc[7]);
+                            gacc[8] = __dp4a((int)t[i].z, sel[0], gacc[8]);   gacc[9] = __dp4a((int)t[i].z, sel[1], gacc[9]);
+                            gacc[10] = __dp4a((int)t[i].z, sel[2], gacc[10]); gacc[11] = __dp4a((int)t[i].z, sel[3], gacc[11]);
+                            gacc[12] = __dp4a((int)t[i].w, sel[0], gacc[12]); gacc[13] = __dp4a((int)t[i].w, sel[1], gacc[13]);
+                            gacc[14] = __dp4a((int)t[i].w, sel[2], gacc[14]); gacc[15] = __dp4a((int)t[i].w, sel[3], gacc[15]);
+                        }
                     }
-                    __syncwarp();
-                    if (i < d) {
-                        if (DUMP && p.dbg.dev_g) p.dbg.dev_g[((size_t)h * p.n_total + story) * d + i] = (float)g_w / (float)(1 << (p.lin_map ? fw : fu));
-                        uvec[i] = (signed char)qi_clamp(a_f + (int)ovec[i], lf);
+    #pragma unroll
+                    for (int o = LPR; o < 32; o <<= 1)
+    #pragma unroll
+                        for (int k = 0; k < 16; k++) gacc[k] += __shfl_xor_sync(0xffffffffu, gacc[k], o);
+                    if (g == 0) {
+                        const uint4 o4 = *reinterpret_cast<const uint4 *>(ovec + 16 * q);
+                        const unsigned ow[4] = {o4.x, o4.y, o4.z, o4.w};
+                        unsigned packed[4];
+    #pragma unroll
+                        for (int w4 = 0; w4 < 4; w4++) {
+                            unsigned v = 0;
+    #pragma unroll
+                            for (int b = 0; b < 4; b++) {
+                                const int g_w = qi_clamp(gacc[4 * w4 + b], lw);
+                                if (DUMP && p.dbg.dev_g && 16u * q + 4 * w4 + b < d)
+                                    p.dbg.dev_g[((size_t)h * p.n_total + story) * d + 16u * q + 4 * w4 + b] = (float)g_w / (float)(1 << fw);
+                                const int a_f = qi_requant(g_w, fw, lf, ff);
+                                v |= ((unsigned)(qi_clamp(a_f + sbyte(ow[w4], b), lf) & 0xFF)) << (8 * b);
+                            }
+                            packed[w4] = v;
+                        }
+                        *reinterpret_cast<uint4 *>(uvec + 16 * q) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    }
+                } else {
+                    const int lw2 = 2 * lw;
+                    const signed char *Hg = reinterpret_cast<const signed char *>(p.img + p.offH[h]);      // int8 [d][HS], L2-resident
+    #pragma unroll 1
+                    for (unsigned i0 = 0; i0 < d; i0 += 32) {
+                        const unsigned i = i0 + lane;
+                        int a_f = 0, g_w = 0;
+                        if (p.lin_map) {
+                            const unsigned *hrow = reinterpret_cast<const unsigned *>(Hg + (size_t)min(i, d - 1) * p.HS);
+                            int s_ = 0;
+                            const unsigned d4 = (d + 3) / 4;
+    #pragma unroll 2
+                            for (unsigned j4 = 0; j4 < d4; j4++) {
+                                const unsigned hw = __ldg(hrow + j4);
+                                const int4 uu = *reinterpret_cast<const int4 *>(ub32 + 4 * j4);
+                                s_ += clamp_biased(shr0m(sbyte_prmt<0>(hw) * uu.x, fb, mb), lw, lw2);
+                                s_ += clamp_biased(shr0m(sbyte_prmt<1>(hw) * uu.y, fb, mb), lw, lw2);
+                                s_ += clamp_biased(shr0m(sbyte_prmt<2>(hw) * uu.z, fb, mb), lw, lw2);
+                                s_ += clamp_biased(shr0m(((int)hw >> 24) * uu.w, fb, mb), lw, lw2);
+                            }
+                            g_w = qi_clamp(s_ - (int)(4u * d4) * lw, lw);
+                            a_f = qi_requant(g_w, fw, lf, ff);
+                        } else if (i < d) {
+                            g_w = (int)uvec[i];
+                            a_f = qi_requant(g_w, fu, lf, ff);
+                        }
+                        __syncwarp();
+                        if (i < d) {
+                            if (DUMP && p.dbg.dev_g) p.dbg.dev_g[((size_t)h * p.n_total + story) * d + i] = (float)g_w / (float)(1 << (p.lin_map ? fw : fu));
+                            uvec[i] = (signed char)qi_clamp(a_f + (int)ovec[i], lf);
+                        }
                     }
                 }
             }

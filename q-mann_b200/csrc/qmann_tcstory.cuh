@@ -142,12 +142,6 @@ __device__ __noinline__ unsigned tc_row_emit(const FwdParams &p, const float (&v
     if (!chunk_irregular<4>(v)) return emit_units_s(unit_mask<4>(v), lane, lane + 32u, 0u, p.DP, ent, cap, base, lt);
     return emit_general_s(p, v, lane, lane + 32u, 0u, ent, cap, base, lt, irregular);
 }
-__device__ __forceinline__ unsigned ldg_na_u16(const void *ptr)
-{
-    unsigned short r;
-    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(ptr));
-    return (unsigned)r;
-}
 
 // (a0, a1) += table codes of this lane's dims 2*lane, 2*lane+1 over entries [beg, end) of the warp's entry list (byte offsets
 // column * DP, DP = 64); table rows in global memory (L2-resident), one coalesced 64-byte row read per entry and warp.
