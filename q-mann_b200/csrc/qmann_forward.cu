@@ -99,6 +99,7 @@ struct qmann_model {
     // tensor-core tier (k_story_tc): fp32 image of the A_h tables [160][V] for the tf32 MMA, its tensor map, geometry
     float *dev_tc_tab = nullptr;
     bool tc_ok = false;
+    bool dense_stream = false;               // QMANN_DENSE_STREAM=1 at create: k_story streams the dense rows itself (staging buffers laid out)
     CUtensorMap tc_tmT;
     unsigned tc_kch = 0, tc_teams = 0, tc_smem = 0;
     // qmann_infer_host staging (grow-only device arenas, two streams)
@@ -557,8 +558,14 @@ static int model_build(qmann_model *m, const qmann_config *cfg, const qmann_weig
         fl.o_uvec = w2(DP); fl.o_ub32 = w2(DP * 4); fl.o_ovec = w2(DP); fl.o_ufl = w2(DP * 4);
         fl.o_zent = w2(16);
         fl.o_brow = w2(c.H * S_pad); fl.o_perm = w2(S_pad * 2); fl.o_cnt = w2(20 * 4);
+        // the staging buffers of the dense stream (4.3 KB per warp at C2) are only laid out when that opt-in mode is on: without
+        // them 24 warps fit beside the tables instead of 20
+        const char *env_ds = getenv("QMANN_DENSE_STREAM"), *env_tc0 = getenv("QMANN_TC");
+        m->dense_stream = env_ds && atoi(env_ds) == 1;
+        // (the tensor-core tier hands what it declines to k_story with the DENSE source, which needs them too)
+        const bool need_stage = m->dense_stream || (env_tc0 && atoi(env_tc0) == 1);
         fl.o_bar = w2(8 * NB, 8);
-        fl.o_stage = w2(NB * fl.buf_bytes, 128);
+        fl.o_stage = w2(need_stage ? NB * fl.buf_bytes : 0u, 128);
         fl.warp_bytes = round_up(o2, 128);
         // entries are 16-bit offsets column * DP
         if ((size_t)(c.V + 1) * DP > 65535u) m->fast_ok = false;
@@ -742,7 +749,8 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
     const bool aligned16 = !in.dev_ids && (((uintptr_t)dev_m | (uintptr_t)dev_q) % 16 == 0);
     // first tier on the tensor cores (k_story_tc): dense arenas, stories of at most 64 sentences
     const bool use_tc = fast && m->tc_ok && aligned16 && b->max_sen <= 64 && b->sum_sen > 0 && b->sum_sen < 0x7FFFFFFFull;
-    const bool stream_dense = use_tc || (fast && aligned16 && (env_stream && atoi(env_stream) == 1));
+    (void)env_stream;
+    const bool stream_dense = use_tc || (fast && aligned16 && m->dense_stream);
     const uint32_t cap = stream_dense ? m->story_chunk_cap : m->chunk_cap;
     unsigned *ctr = m->dev_counter;
     for (uint32_t s0 = first; s0 < first + count; s0 += cap) {
