@@ -1448,6 +1448,14 @@ extern "C" {
 
 const char *qmann_bigmem_last_error(void) { return g_berr.c_str(); }
 
+// inside qmann_bigmem_create, after the object exists: a CUDA failure releases whatever was allocated so far (an out-of-memory failure
+// while creating a large shard must not leak GBs)
+#define BCUDA_B(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) { qmann_bigmem_destroy(b); return bfail(QMANN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } \
+    } while (0)
+void qmann_bigmem_destroy(qmann_bigmem *b);
 int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann_weights *w, const int8_t *const *dev_M,
                         const int8_t *const *dev_C, uint64_t S_total, uint64_t slot0, uint64_t S_local, uint32_t Q_max)
 {
@@ -1473,11 +1481,11 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
     memset(b, 0, sizeof(*b));
     b->cfg = c;
     int dev = 0;
-    BCUDA(cudaGetDevice(&dev));
+    BCUDA_B(cudaGetDevice(&dev));
     cudaDeviceProp prop;
-    BCUDA(cudaGetDeviceProperties(&prop, dev));
+    BCUDA_B(cudaGetDeviceProperties(&prop, dev));
     b->sm_count = prop.multiProcessorCount;
-    BCUDA(cudaDeviceGetAttribute(&b->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    BCUDA_B(cudaDeviceGetAttribute(&b->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     b->S_total = S_total; b->slot0 = slot0; b->S_local = S_local; b->Q_max = Q_max;
     unsigned la_max = 0;
     for (unsigned h = 0; h < c.H; h++) {
@@ -1491,33 +1499,33 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
     }
     b->bias = (c.mode == 3) ? 127u * c.d : la_max;
     b->NB = 2 * b->bias + 1;
-    if (b->NB > 65536) { delete b; return bfail(QMANN_E_ARG, "score range does not fit 16-bit bins (mode 3 needs d <= 258)"); }
+    if (b->NB > 65536) { qmann_bigmem_destroy(b); return bfail(QMANN_E_ARG, "score range does not fit 16-bit bins (mode 3 needs d <= 258)"); }
     b->dev_W = w->dev_W;
     const size_t Qd = (size_t)Q_max * c.d;
-    BCUDA(cudaMalloc((void **)&b->u_a, Qd));
-    BCUDA(cudaMalloc((void **)&b->u_b, Qd));
-    BCUDA(cudaMalloc((void **)&b->ub, Qd * 4));
-    BCUDA(cudaMalloc((void **)&b->av, Qd * 4));
-    BCUDA(cudaMalloc((void **)&b->sv, Qd * 4));
-    BCUDA(cudaMalloc((void **)&b->ub8, Qd));
-    BCUDA(cudaMalloc((void **)&b->umax, (size_t)Q_max * 4));
+    BCUDA_B(cudaMalloc((void **)&b->u_a, Qd));
+    BCUDA_B(cudaMalloc((void **)&b->u_b, Qd));
+    BCUDA_B(cudaMalloc((void **)&b->ub, Qd * 4));
+    BCUDA_B(cudaMalloc((void **)&b->av, Qd * 4));
+    BCUDA_B(cudaMalloc((void **)&b->sv, Qd * 4));
+    BCUDA_B(cudaMalloc((void **)&b->ub8, Qd));
+    BCUDA_B(cudaMalloc((void **)&b->umax, (size_t)Q_max * 4));
     {
         // tensor-core scorer: d a multiple of 64 whose query planes (d * 256 bytes per block of 64 queries) fit shared memory
         const char *env_mma = getenv("QMANN_BIGMEM_MMA");
         const size_t frag_bytes = (size_t)c.d * 256;
         b->mma_ok = c.mode == 2 && c.frac_bin == 2 && c.d % 64 == 0 && frag_bytes + 256 + (size_t)2 * 2 * 16 * c.d <= (size_t)b->smem_optin &&
                     !(env_mma && atoi(env_mma) == 0);
-        if (b->mma_ok) BCUDA(cudaMalloc((void **)&b->bfrag, (size_t)((Q_max + MMA_QB - 1) / MMA_QB) * frag_bytes));
+        if (b->mma_ok) BCUDA_B(cudaMalloc((void **)&b->bfrag, (size_t)((Q_max + MMA_QB - 1) / MMA_QB) * frag_bytes));
     }
     b->bin8 = (b->NB <= 256) ? 1 : 0;                                  // mode 2: 2*127+1 bins fit a byte
-    BCUDA(cudaMalloc((void **)&b->bins, std::max<size_t>(16, (size_t)Q_max * S_local * (b->bin8 ? 1 : 2))));
-    BCUDA(cudaMalloc((void **)&b->pq, (size_t)Q_max * b->NB));
-    BCUDA(cudaMalloc((void **)&b->thr, (size_t)Q_max * 4));
-    BCUDA(cudaMalloc((void **)&b->nsel, (size_t)Q_max * 4));
-    if (c.V) BCUDA(cudaMalloc((void **)&b->zbuf, (size_t)Q_max * c.V * 4));
+    BCUDA_B(cudaMalloc((void **)&b->bins, std::max<size_t>(16, (size_t)Q_max * S_local * (b->bin8 ? 1 : 2))));
+    BCUDA_B(cudaMalloc((void **)&b->pq, (size_t)Q_max * b->NB));
+    BCUDA_B(cudaMalloc((void **)&b->thr, (size_t)Q_max * 4));
+    BCUDA_B(cudaMalloc((void **)&b->nsel, (size_t)Q_max * 4));
+    if (c.V) BCUDA_B(cudaMalloc((void **)&b->zbuf, (size_t)Q_max * c.V * 4));
     for (unsigned h = 0; h < c.H; h++) {
         if (!c.lin_map) continue;
-        BCUDA(cudaMalloc((void **)&b->dev_H[h], (size_t)c.d * c.d));
+        BCUDA_B(cudaMalloc((void **)&b->dev_H[h], (size_t)c.d * c.d));
         k_big_quant_H<<<64, 256>>>(w->dev_Hm[h], b->dev_H[h], c.d * c.d, c.iwl_w[h], c.frac_w[h]);
         count_launch();
     }
@@ -1530,15 +1538,15 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
                            !(env_fast && atoi(env_fast) == 0);
     if (want_fast) {
         unsigned *dev_flag = nullptr;
-        BCUDA(cudaMalloc((void **)&dev_flag, 4));
+        BCUDA_B(cudaMalloc((void **)&dev_flag, 4));
         const unsigned gx = (unsigned)std::min<unsigned long long>((S_local + 7) / 8, (unsigned long long)b->sm_count * 16);
         for (unsigned h = 0; h < c.H; h++) {
-            BCUDA(cudaMalloc((void **)&b->rowmax[h], S_local));
-            BCUDA(cudaMemset(dev_flag, 0, 4));
+            BCUDA_B(cudaMalloc((void **)&b->rowmax[h], S_local));
+            BCUDA_B(cudaMemset(dev_flag, 0, 4));
             k_big_prep_mem<<<std::max(1u, gx), 256>>>(b->M[h], S_local, c.d, b->f[h], nullptr, b->rowmax[h], dev_flag);
             count_launch();
             unsigned flag = 0;
-            BCUDA(cudaMemcpy(&flag, dev_flag, 4, cudaMemcpyDeviceToHost));
+            BCUDA_B(cudaMemcpy(&flag, dev_flag, 4, cudaMemcpyDeviceToHost));
             b->Y[h] = b->M[h];
             if (flag) {
                 if (cudaMalloc((void **)&b->Y_own[h], (size_t)S_local * c.d) != cudaSuccess) {
@@ -1552,7 +1560,7 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
             }
             b->fast[h] = true;
         }
-        BCUDA(cudaDeviceSynchronize());
+        BCUDA_B(cudaDeviceSynchronize());
         cudaFree(dev_flag);
     }
     {
@@ -1562,10 +1570,10 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
         bool ok = b->mma_ok && c.d % 128 == 0 && c.d >= 128 && need <= (size_t)b->smem_optin && !(env_tc && atoi(env_tc) == 0);
         for (unsigned h = 0; h < c.H && ok; h++)
             if (b->fast[h]) ok = tmap_bytes_rows(&b->tmY[h], b->Y[h], S_local, c.d);
-        if (ok) BCUDA(cudaMalloc((void **)&b->bplanes, (size_t)((Q_max + TCS_QB - 1) / TCS_QB) * (c.d / 128) * 4 * 8192));
+        if (ok) BCUDA_B(cudaMalloc((void **)&b->bplanes, (size_t)((Q_max + TCS_QB - 1) / TCS_QB) * (c.d / 128) * 4 * 8192));
         b->tc_ok = ok;
     }
-    BCUDA(cudaDeviceSynchronize());
+    BCUDA_B(cudaDeviceSynchronize());
     *out = b;
     return QMANN_OK;
 }
