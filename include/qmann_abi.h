@@ -154,6 +154,12 @@ typedef struct {
     uint32_t iwl_w[QMANN_MAX_HOP], frac_w[QMANN_MAX_HOP];       /* weight layers     MemN2N.c:718-754 */
     uint32_t iwl_att[QMANN_MAX_HOP], frac_att[QMANN_MAX_HOP];   /* addressing        MemN2N.c:721-722 */
     uint32_t iwl_bin, frac_bin;                                 /* u operand         MemN2N.c:767-773 */
+    /* optional layers of the reference's graph, default off (zero): */
+    uint32_t en_sc_att;               /* EN_SC_ATT (define.h:58): scale layer between scorer and softmax, s' = s * w_h in fp32
+                                         (scale_fwd, lib/layer.c:4450; MemN2N.c:852, 2446, 2647)                             */
+    float    sc_att_w[QMANN_MAX_HOP]; /* its one weight per hop (scale.w)                                                      */
+    uint32_t en_non_lin;              /* EN_NON_LINEARITY (define.h:294): RELU activation layer after the hop update,
+                                         u' = Q_(iwl[h],frac[h])(max(u', 0)) (activation_fwd, MemN2N.c:894, 2670)              */
 } qmann_config;
 
 /* Device pointers to the fp32 weights as they live in the reference's layer structs

@@ -30,6 +30,7 @@ void cuda_data_in(float *dev_m, float *dev_q, float *dev_a, float *m, float *q, 
 void cuda_data_destructor(float *dev_m, float *dev_q, float *dev_a);
 void cuda_copy_dev2host(float *host, float *dev, unsigned int size);
 void cuda_dense_init(float *dev_out_vec, float *dev_grad_out, float *dev_w_mat_del, float *dev_w_mat, float *dev_bias, float *dev_bias_del, float *w_mat, float *bias, float *dev_f_overflow, unsigned int dim_in, unsigned int dim_out);
+void cuda_scale_init(float *dev_w, float *dev_w_del, float *dev_out, float *dev_grad_out, float *w, unsigned int dim);
 void cuda_dense_mat_init(float *dev_out_mat, float *dev_grad_out, float *dev_w_mat, float *dev_w_mat_del, float *dev_bias, float *dev_bias_del, float *w_mat, float *bias, float *dev_f_overflow, unsigned int dim_in, unsigned int dim_out, unsigned int dim_len);
 
 static void die(const char *msg) { fprintf(stderr, "ref_harness: %s\n", msg); exit(2); }
@@ -71,6 +72,16 @@ int main(int argc, char **argv)
     rd(n_sen, 4, N, fc);
     float *m = falloc((size_t)sum_sen * V), *q = falloc((size_t)N * V), *a = falloc((size_t)N * V);
     rd(m, 4, (size_t)sum_sen * V, fc); rd(q, 4, (size_t)N * V, fc); rd(a, 4, (size_t)N * V, fc);
+    /* optional extension: the default-off layers of the reference's graph (EN_SC_ATT, EN_NON_LINEARITY; MemN2N.c:852, 894) */
+    uint32_t en_sc_att = 0, en_non_lin = 0;
+    float sc_w[MAXH] = {0};
+    {
+        char ext[8];
+        if (fread(ext, 1, 8, fc) == 8) {
+            if (memcmp(ext, "QMNEXT01", 8)) die("bad extension magic");
+            rd(&en_sc_att, 4, 1, fc); rd(sc_w, 4, H, fc); rd(&en_non_lin, 4, 1, fc);
+        }
+    }
     fclose(fc);
 
     FILE *fp_log = fopen("/dev/null", "w");
@@ -81,6 +92,8 @@ int main(int argc, char **argv)
     dot_mat_vec dotmv[MAXH], w_sum[MAXH];
     softmax sf_in[MAXH], sf_out;
     sum_vec sv[MAXH];
+    scale sc_sf_in[MAXH];
+    activation non_lin[MAXH];
     cross_entropy ce;
 
     dense_constructor(&emb_q, V, d, true, 40.0f, "NULL", f_fixed, iwl_w[0], frac_w[0], iwl_w[0], frac_w[0], f_mode, fp_log);
@@ -91,11 +104,13 @@ int main(int argc, char **argv)
             dot_mat_vec_constructor(&dotmv[h], S_max, d, d, false, f_fixed, iwl_att[h], frac_att[h], iwl_bin, frac_bin, f_mode, mode, fp_log);
         else
             dot_mat_vec_constructor(&dotmv[h], S_max, d, d, false, f_fixed, iwl_att[h], frac_att[h], iwl_att[h], frac_att[h], f_mode, mode, fp_log);
+        if (en_sc_att) scale_constructor(&sc_sf_in[h], S_max, f_fixed, iwl_att[h], frac_att[h], f_mode, fp_log);      /* MemN2N.c:852-854 */
         softmax_constructor(&sf_in[h], S_max, false, false, fp_log);
         dot_mat_vec_constructor(&w_sum[h], S_max, d, S_max, true, f_fixed, iwl[h], frac[h], iwl[h], frac[h], f_mode, mode, fp_log);
         if (lin_map)
             dense_constructor(&lin[h], d, d, true, 20.0f, "NULL", f_fixed, iwl_bin, frac_bin, iwl_w[h], frac_w[h], f_mode, fp_log);
         sum_vec_constructor(&sv[h], d, f_fixed, iwl[h], frac[h], f_mode, fp_log);
+        if (en_non_lin) activation_constructor(&non_lin[h], d, "RELU", f_fixed, iwl[h], frac[h], f_mode, fp_log);    /* MemN2N.c:894-896 */
     }
     dense_constructor(&ds_ans, d, V, true, 40.0f, "NULL", false, 8, 7, 8, 7, f_mode, fp_log);
     softmax_constructor(&sf_out, V, false, false, fp_log);
@@ -123,6 +138,12 @@ int main(int argc, char **argv)
             cuda_dense_init(lin[h].dev_out_vec, lin[h].dev_grad_out, lin[h].dev_w_mat_del, lin[h].dev_w_mat, lin[h].dev_bias, lin[h].dev_bias_del, lin[h].w_mat[0], lin[h].bias, lin[h].dev_f_overflow, lin[h].dim_in, lin[h].dim_out);
         }
         sum_vec_init(&sv[h]);
+        if (en_sc_att) {
+            scale_init(&sc_sf_in[h]);                       /* random weight; replace it by the case's and upload again */
+            *(sc_sf_in[h].w) = sc_w[h];
+            cuda_scale_init(sc_sf_in[h].dev_w, sc_sf_in[h].dev_w_del, sc_sf_in[h].dev_out, sc_sf_in[h].dev_grad_out, sc_sf_in[h].w, sc_sf_in[h].dim_max);
+        }
+        if (en_non_lin) activation_init(&non_lin[h]);
     }
     dense_init(&ds_ans);
     memcpy(ds_ans.w_mat[0], W, sizeof(float) * V * d);
@@ -165,6 +186,10 @@ int main(int argc, char **argv)
                 dense_mat_in(&emb_m[h], ns, hm, hm, dev_m + addr_m * V, NULL);
                 dense_mat_in(&emb_c[h], ns, hm, hm, dev_m + addr_m * V, NULL);
                 dot_mat_vec_in(&dotmv[h], ns, hm, hv, hv, emb_m[h].dev_out_mat, dev_u, NULL);
+                if (en_sc_att) {                                /* MemN2N.c:2446-2448 */
+                    scale_in(&sc_sf_in[h], ns, hv, hv, dotmv[h].dev_out_vec, NULL);
+                    softmax_in(&sf_in[h], ns, hv, hv, sc_sf_in[h].dev_out, NULL);
+                } else
                 softmax_in(&sf_in[h], ns, hv, hv, dotmv[h].dev_out_vec, NULL);
                 dot_mat_vec_in(&w_sum[h], ns, hm, hv, hv, emb_c[h].dev_out_mat, sf_in[h].dev_out_vec, NULL);
                 float *dev_a_in = dev_u;
@@ -174,6 +199,10 @@ int main(int argc, char **argv)
                 }
                 sum_vec_in(&sv[h], hv, hv, hv, dev_a_in, w_sum[h].dev_out_vec, NULL);
                 dev_u = sv[h].dev_out_vec;
+                if (en_non_lin) {                               /* MemN2N.c:2423-2431: the next hop reads non_lin[h].out */
+                    activation_in(&non_lin[h], hv, hv, sv[h].dev_out_vec, NULL);
+                    dev_u = non_lin[h].dev_out;
+                }
             }
             dense_in(&ds_ans, hv, hv, dev_u, NULL);
             softmax_in(&sf_out, V, hv, hv, ds_ans.dev_out_vec, NULL);
@@ -186,10 +215,12 @@ int main(int argc, char **argv)
                 dense_mat_fwd(&emb_m[h], false);
                 dense_mat_fwd(&emb_c[h], false);
                 dot_mat_vec_fwd(&dotmv[h], false);
+                if (en_sc_att) scale_fwd(&sc_sf_in[h], false);              /* MemN2N.c:2647 */
                 softmax_fwd(&sf_in[h], false);
                 dot_mat_vec_fwd(&w_sum[h], false);
                 if (lin_map) dense_fwd(&lin[h], false);
                 sum_vec_fwd(&sv[h], false);
+                if (en_non_lin) activation_fwd(&non_lin[h], false);         /* MemN2N.c:2670 */
                 if (dump) {
                     const size_t so = (size_t)h * sum_sen + addr_m, vo = ((size_t)h * N + i) * d;
                     if (ns) {
@@ -200,7 +231,7 @@ int main(int argc, char **argv)
                     }
                     cuda_copy_dev2host(o_o + vo, w_sum[h].dev_out_vec, d);
                     if (lin_map) cuda_copy_dev2host(o_g + vo, lin[h].dev_out_vec, d);
-                    cuda_copy_dev2host(o_u + vo, sv[h].dev_out_vec, d);
+                    cuda_copy_dev2host(o_u + vo, en_non_lin ? non_lin[h].dev_out : sv[h].dev_out_vec, d);
                 }
             }
             dense_fwd(&ds_ans, false);
@@ -243,6 +274,8 @@ int main(int argc, char **argv)
         dot_mat_vec_destructor(&dotmv[h]); softmax_destructor(&sf_in[h]); dot_mat_vec_destructor(&w_sum[h]);
         if (lin_map) dense_destructor(&lin[h]);
         sum_vec_destructor(&sv[h]);
+        if (en_sc_att) scale_destructor(&sc_sf_in[h]);
+        if (en_non_lin) activation_destructor(&non_lin[h]);
     }
     dense_destructor(&ds_ans); softmax_destructor(&sf_out); cross_entropy_destructor(&ce);
     return 0;

@@ -381,6 +381,8 @@ static int model_build(qmann_model *m, const qmann_config *cfg, const qmann_weig
         p.ff[h] = c.frac[h]; p.iff[h] = c.iwl[h]; p.lf[h] = fixed_max(c.iwl[h], c.frac[h]);
     }
     p.fb = c.frac_bin; p.lb = fixed_max(c.iwl_bin, c.frac_bin);
+    p.en_sc_att = c.en_sc_att ? 1 : 0; p.en_non_lin = c.en_non_lin ? 1 : 0;
+    for (unsigned h = 0; h < c.H; h++) p.sc_w[h] = c.sc_att_w[h];
 
     // ---- per-warp scratch layout ----
     const unsigned S_pad = round_up(c.S_max, 32);
@@ -501,7 +503,8 @@ static int model_build(qmann_model *m, const qmann_config *cfg, const qmann_weig
             if (c.iwl_w[h] < 1) unit_ok = false;
         }
         m->nmax = unit_ok ? nmax : 0;
-        m->fast_ok = unit_ok;
+        // the optional layers (scale before the softmax, RELU after the update) exist in the general kernel only
+        m->fast_ok = unit_ok && !c.en_sc_att && !c.en_non_lin;
         // n unit entries stand for a count n only while n * max|code| stays inside EVERY hop's weight format
         // (the reference clamps each product Q_w(Q_w(n) * Q_w(T)) to that hop's limit, lib/layer_cuda.cu:120)
         unsigned sl = 127;

@@ -107,6 +107,10 @@ struct FwdParams {
     int fast_softmax;                      // attention codes from a float total when no weight is near a truncation boundary
     unsigned pf_dist, pf_mode;             // L2 prefetch of the story pf_dist claims ahead (0: off, 1: bulk prefetch, 2: per line)
     unsigned long long *path_count;        // [3] stories that entered the packed, unpacked and general tier
+    // optional layers (general kernel only; the production tiers are switched off when either is on)
+    int en_sc_att;                         // EN_SC_ATT: s' = s * sc_w[h] in fp32 between scorer and softmax (lib/layer_cuda.cu:4805)
+    float sc_w[MAXH];
+    int en_non_lin;                        // EN_NON_LINEARITY: RELU + Q_f after the hop update (lib/layer_cuda.cu:4548)
 };
 
 // =============================================================================================
@@ -1026,13 +1030,13 @@ __global__ void __launch_bounds__(512, 1) k_forward(const __grid_constant__ FwdP
                 } else {
                     sv = (float)sc[r] / (float)(1 << fa);
                 }
+                if (DEBUG && p.dbg.dev_s) p.dbg.dev_s[(size_t)h * p.sum_sen + soff + r] = sv;      // the scorer's output (before the scale layer)
+                if (p.en_sc_att) sv = __fmul_rn(sv, p.sc_w[h]);     // scale layer (EN_SC_ATT): out = in * w, fp32, not quantised (lib/layer_cuda.cu:4805-4822)
                 ex[r] = sv;
                 mx = fmaxf(mx, sv);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (DEBUG && p.dbg.dev_s)
-                for (unsigned r = lane; r < S; r += 32) p.dbg.dev_s[(size_t)h * p.sum_sen + soff + r] = ex[r];
             for (unsigned r = lane; r < S; r += 32) ex[r] = __expf(ex[r] - mx);
             __syncwarp();
             double total = 0.0;
@@ -1133,7 +1137,8 @@ __global__ void __launch_bounds__(512, 1) k_forward(const __grid_constant__ FwdP
                 }
                 __syncwarp();
                 if (i < d) {
-                    const int un = qi_clamp(a_f + (int)ovec[i], lf);
+                    int un = qi_clamp(a_f + (int)ovec[i], lf);
+                    if (p.en_non_lin) un = max(un, 0);              // activation layer (EN_NON_LINEARITY): Q_f(RELU(u')), on the grid already (lib/layer_cuda.cu:4548)
                     if (DEBUG) {
                         const size_t vo = ((size_t)h * p.n_total + story) * d + i;
                         if (p.dbg.dev_o) p.dbg.dev_o[vo] = (float)ovec[i] / (float)(1 << ff);

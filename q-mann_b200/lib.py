@@ -25,7 +25,8 @@ class QConfig(C.Structure):
     _fields_ = [("V", _U32), ("d", _U32), ("S_max", _U32), ("H", _U32), ("mode", _U32), ("lin_map", _U32),
                 ("const_scale", C.c_int32),
                 ("iwl", _U32 * MAX_HOP), ("frac", _U32 * MAX_HOP), ("iwl_w", _U32 * MAX_HOP), ("frac_w", _U32 * MAX_HOP),
-                ("iwl_att", _U32 * MAX_HOP), ("frac_att", _U32 * MAX_HOP), ("iwl_bin", _U32), ("frac_bin", _U32)]
+                ("iwl_att", _U32 * MAX_HOP), ("frac_att", _U32 * MAX_HOP), ("iwl_bin", _U32), ("frac_bin", _U32),
+                ("en_sc_att", _U32), ("sc_att_w", C.c_float * MAX_HOP), ("en_non_lin", _U32)]
 
 
 class QWeights(C.Structure):
@@ -146,6 +147,11 @@ def make_config(cfg) -> QConfig:
         q.iwl_w[h], q.frac_w[h] = f["iwl_w"][h], f["frac_w"][h]
         q.iwl_att[h], q.frac_att[h] = f["iwl_att"][h], f["frac_att"][h]
     q.iwl_bin, q.frac_bin = f["iwl_bin"], f["frac_bin"]
+    sc = getattr(cfg, "sc_att", None)
+    q.en_sc_att = 1 if sc is not None else 0
+    for h in range(cfg.H):
+        q.sc_att_w[h] = float(sc[h]) if sc is not None else 0.0
+    q.en_non_lin = 1 if getattr(cfg, "non_lin", False) else 0
     return q
 
 

@@ -37,6 +37,8 @@ class ModelConfig:
     en_mq: bool = True          # EN_MQ, define.h:79
     V_dict: int = 0             # dictionary size (incl. NULL at 0); time columns are V_dict..V-1
     wl: int = BW_WL             # word length BW_WL (define.h:21); < 8 gives formats narrower than a byte
+    sc_att: Optional[List[float]] = None   # EN_SC_ATT (define.h:58): the scale layer's weight per hop, None = layer absent
+    non_lin: bool = False       # EN_NON_LINEARITY (define.h:294): RELU activation layer after every hop update
 
     def formats(self) -> Dict[str, List[int]]:
         """Per-hop (iwl, frac) arrays exactly as MemN2N.c:714-775 computes them."""
@@ -220,6 +222,12 @@ def write_case(path: str, cfg: ModelConfig, w: Weights, st: Stories) -> None:
         fo.write(np.ascontiguousarray(st.n_sen, dtype="<u4").tobytes())
         for t in (st.m, st.q, st.a):
             fo.write(np.ascontiguousarray(t, dtype="<f4").tobytes())
+        if cfg.sc_att is not None or cfg.non_lin:
+            # optional-layer extension read by oracle/ref_harness.c when present
+            fo.write(b"QMNEXT01")
+            fo.write(struct.pack("<I", 1 if cfg.sc_att is not None else 0))
+            fo.write(np.asarray(cfg.sc_att if cfg.sc_att is not None else [0.0] * cfg.H, dtype="<f4").tobytes())
+            fo.write(struct.pack("<I", 1 if cfg.non_lin else 0))
 
 
 def read_dump(path: str) -> Dict[str, np.ndarray]:

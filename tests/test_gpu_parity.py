@@ -360,3 +360,38 @@ def test_optional_layer_variants_match_reference_library_live(qmann):
             o = torch.zeros(d, device="cuda"); L.cuda_dense_fwd(Wm.data_ptr(), None, xv.data_ptr(), o.data_ptr(), None, S, d, kind, True, 5, 2, 5, 2, 3, False); return o
         both(f"dense activation={kind.decode()}", dense_act)
     assert len(checked) >= 25
+
+
+@pytest.mark.parametrize("preset,mode,sc,non_lin", [("C1", 2, [0.37, -1.5, 2.25], False), ("C1", 2, None, True), ("C2", 2, [1.0, 0.5, 3.0], True),
+                                                    ("C3", 3, [0.8, 1.7, -0.6], True), ("C4", 2, [0.25, 4.0, 1.0], True)])
+def test_batched_optional_layers_match_reference_live(preset, mode, sc, non_lin, qmann, synth):
+    """the default-off layers of the reference's graph in the BATCHED forward -- the scale layer between
+    scorer and softmax (EN_SC_ATT, MemN2N.c:852, 2446, 2647; s' = s * w in fp32) and the RELU activation after the hop
+    update (EN_NON_LINEARITY, MemN2N.c:894, 2423, 2670) -- against the reference's own layer objects run live with those
+    layers wired in (oracle/ref_harness.c): every tensor of the graph, predictions and match count."""
+    from test_gpu_production import REF_EXE, _ref_live
+    if not os.path.exists(REF_EXE):
+        pytest.skip("oracle/_ref/ref_harness_refcuda not built (needs /root/reference at build time)")
+    cfg = synth.preset_config(preset)
+    cfg.mode, cfg.sc_att, cfg.non_lin = mode, sc, non_lin
+    w = synth.make_weights(cfg, 300 + mode, sigma=0.5)
+    st = synth.make_stories(cfg, 600, 301, S=min(cfg.S_max, 50), ragged=True)
+    ref = _ref_live(synth, cfg, w, st)
+    got = _fwd(qmann, cfg, w, st)
+    tag = f"{preset}/mode{mode}/sc={sc}/relu={non_lin}"
+    _assert_fixed_equal(got, ref, cfg, tag)
+    np.testing.assert_array_equal(got["z"], ref["z"], err_msg=f"{tag}: answer logits")
+    np.testing.assert_allclose(got["p"], ref["p"], rtol=SOFTMAX_RTOL, atol=0, err_msg=f"{tag}: attention weights")
+    np.testing.assert_array_equal(got["pred"], ref["pred"], err_msg=tag)
+    assert got["match"] == int(ref["match"])
+    if non_lin:
+        assert (got["u"] >= 0).all() and (ref["u"] >= 0).all(), "RELU output"
+    # the production entry (no debug struct) takes the same general kernel when an optional layer is on
+    plain = _fwd(qmann, cfg, w, st, debug=False, want_h=False)
+    np.testing.assert_array_equal(plain["pred"], ref["pred"], err_msg=f"{tag}: production entry")
+    assert plain["match"] == int(ref["match"])
+    # and the layers change the result (the test would be vacuous otherwise)
+    base_cfg = synth.preset_config(preset)
+    base_cfg.mode = mode
+    base = _fwd(qmann, base_cfg, w, st)
+    assert not np.array_equal(base["u"], got["u"])
