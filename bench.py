@@ -724,6 +724,20 @@ def main():
     assert np.array_equal(pred_h, pred_dev), "end-to-end predictions differ from the device-resident pass"
     assert match_h == int((pred_h == st.ans).sum())
     d2h = int(4 * n + 4)
+    # the ceiling of that figure: the same bytes as one plain pinned-host -> device copy, all ranks at the same time (the ranks of a box
+    # share the host's memory and PCIe root complexes)
+    copy_gbs = None
+    if not use_ids:
+        stage = torch.empty_like(db.m)
+        for _ in range(2):
+            stage.copy_(m_pin, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            stage.copy_(m_pin, non_blocking=True)
+        torch.cuda.synchronize()
+        copy_gbs = 3 * st.m.nbytes / (time.perf_counter() - t0) / 1e9
+        del stage
 
     # ---------------- the same step with weights that saturate more (which tier finishes how many stories) ----------------
     def timed_steps(mdl, dbatch, k):
@@ -782,9 +796,10 @@ def main():
     ms_step = ms_total / K
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms_step, e2e_ms, ms_compact / max(1, pairs), ms_forward / max(1, pairs), e2e_ids["ms_per_step"] if e2e_ids else 0.0],
-                         dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([ms_step, e2e_ms, ms_compact / max(1, pairs), ms_forward / max(1, pairs), e2e_ids["ms_per_step"] if e2e_ids else 0.0,
+                          -(copy_gbs or 0.0)], dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        copy_gbs = -float(t[5]) if copy_gbs else None          # the slowest rank's copy rate
         ms_step, e2e_ms = float(t[0]), float(t[1])
         k_compact_ms, k_forward_ms = float(t[2]), float(t[3])
         if e2e_ids:
@@ -864,6 +879,9 @@ def main():
                              f"inputs {bytes_story * n / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "h2d_GB/s_per_rank": h2d / (e2e_ms / 1e3) / 1e9,
+                    "host_copy_ceiling_GB/s_per_rank": copy_gbs,
+                    "frac_of_host_copy_ceiling": (h2d / (e2e_ms / 1e3) / 1e9 / copy_gbs) if copy_gbs else None,
                     "steps": Ke, "api": ("qmann_infer_ids_host (pinned host id lists in, host predictions + match count out)" if use_ids else
                             "qmann_infer_host (pinned host arenas in, host predictions + match count out)")},
             "gpu_launches": int(launches),
