@@ -666,15 +666,6 @@ __device__ __forceinline__ void umma_i8(unsigned d_tmem, unsigned long long a_de
         : "memory");
 }
 
-// one (slot, query) score in the reference order of operations: every product truncated and saturated before the sum
-__device__ __noinline__ int big_exact_score(const signed char *__restrict__ yr, const signed char *__restrict__ ur, unsigned d, int la, int fb)
-{
-    int sp = 0;
-#pragma unroll 4
-    for (unsigned t = 0; t < d; t++) sp += qi_mul((int)yr[t], (int)ur[t], la, fb);
-    return qi_clamp(sp, la);
-}
-
 __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __grid_constant__ TcScoreParams p)
 {
     using namespace qtc;
@@ -911,6 +902,314 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __gri
     if (warp == TCS_W_MMA) tmem_dealloc(tmem, 128);
 }
 
+// -------------------------------------------------------------------------------------------------
+// k_big_scores_tq: k_big_scores_tc with the operand roles swapped -- the QUERIES are the A operand and live in tensor memory,
+// the memory tile is the B operand (d = 128 or 256, byte bins).
+//
+//   D[128 queries][128 slots] (int32, TMEM) += A[128 queries][K] (TMEM: lane = query, four 8-bit K elements per column)
+//                                              * B[128 slots][K]^T (shared memory, K-major, 128-byte swizzle)
+//
+// What that buys over k_big_scores_tc:
+//   * the four query planes (4 x d bytes per query = 256 TMEM columns at d = 256) take no shared memory, so a CTA serves 128 queries
+//     per pass over the memory instead of 64: the indicator planes of a tile -- the builders' work, the largest cost of the tc
+//     kernel -- are built once per 128 queries, and one tcgen05.mma (M128 N128 K32) does twice the work per issue;
+//   * an epilogue lane owns a QUERY and reads 64 consecutive slots of it from its TMEM lane: the score bins leave as 64 contiguous
+//     bytes per lane without a shared-memory transpose.
+// TMEM: accumulator tiles at columns [0,128) and [128,256), query planes at 256 + (kc * 4 + plane) * 32 + k / 4.
+// Warp roles and the mbarrier protocol are those of k_big_scores_tc; the plane ring is three deep (the shared memory the query
+// planes no longer take).
+// (A variant with the score histogram fused into this epilogue was measured and dropped: with a lane per query every lane of a
+// shared-memory atomic hits its own address, ~12 cycles per warp instruction, 6.4 k cycles per tile against 3.1 k of MMA issue;
+// lane-exclusive counters without atomics need one epilogue warp per quadrant, whose dependent load-add-store chains took 9 k.)
+// -------------------------------------------------------------------------------------------------
+constexpr unsigned TQ_QB = 128, TQ_NP = 3;
+
+struct TqScoreParams {
+    alignas(64) CUtensorMap tmY;     // Y as bytes [S_local][d], box 128 x 128, 128-byte swizzle
+    const signed char *Y;
+    const unsigned char *rowmax;
+    unsigned long long S_local;
+    unsigned d, Q;
+    int la, fb;
+    const signed char *ub8;
+    const unsigned *umax;
+    unsigned char *bins;
+    unsigned bias;
+    unsigned long long *clk;         // QMANN_TC_TRACE builds: per-role cycle accumulators of CTA (0, 0)
+};
+
+__device__ __forceinline__ void umma_i8_ts(unsigned d_tmem, unsigned a_tmem, unsigned long long b_desc, unsigned idesc, unsigned accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// plane a = 1..3 of four packed query codes: -sgn(u) ((a (|u| & 3)) & 3); plane 0 is u itself
+__device__ __forceinline__ unsigned query_plane_word(unsigned uw, unsigned pl)
+{
+    if (pl == 0) return uw;
+    unsigned fill;
+    asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(fill) : "r"(uw));           // 0xFF in the bytes that are negative
+    const unsigned a = (((uw ^ fill) & 0x03030303u) + (fill & 0x01010101u)) & 0x03030303u;    // |u| & 3 per byte
+    const unsigned a0 = a & 0x01010101u;
+    const unsigned m = (pl == 1) ? a : (pl == 2 ? (a0 << 1) : ((a + (a0 << 1)) & 0x03030303u));
+    return (fill & m) | (~fill & __vneg4(m));
+}
+
+__global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tq(const __grid_constant__ TqScoreParams p)
+{
+    using namespace qtc;
+    extern __shared__ __align__(16) unsigned char sm[];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned KC = p.d / 128;                                     // K chunks per tile
+    const unsigned sraw = smem_u32(sm), sbase = (sraw + 1023u) & ~1023u;
+    unsigned char *gbase = sm + (sbase - sraw);
+    // layout: [Y ring: 3 x 16 KB][plane ring: 3 x 3 x 16 KB][control, 1 KB]
+    const unsigned yrg = sbase, prg = yrg + TCS_NY * TCS_TILE, cb = prg + TQ_NP * 3u * TCS_TILE;
+    unsigned char *cbg = gbase + (cb - sbase);
+    const unsigned bar_yfull = cb, bar_yfree = cb + 24, bar_built = cb + 48, bar_pfree = cb + 72, bar_dfull = cb + 96, bar_dfree = cb + 112, tmem_slot = cb + 128;
+    unsigned *umax_s = reinterpret_cast<unsigned *>(cbg + 256);        // [128]
+    const unsigned q0 = blockIdx.y * TQ_QB;
+    for (unsigned i = threadIdx.x; i < TQ_QB; i += blockDim.x) umax_s[i] = (q0 + i < p.Q) ? p.umax[q0 + i] : 0u;
+    if (threadIdx.x == 0) {
+        for (unsigned s = 0; s < TCS_NY; s++) { mbar_init(bar_yfull + 8 * s, 1); mbar_init(bar_yfree + 8 * s, 1); }
+        for (unsigned s = 0; s < TQ_NP; s++) { mbar_init(bar_built + 8 * s, TCS_BUILDERS); mbar_init(bar_pfree + 8 * s, 1); }
+        for (unsigned s = 0; s < 2; s++) { mbar_init(bar_dfull + 8 * s, 1); mbar_init(bar_dfree + 8 * s, TCS_EPI); }
+        mbar_fence_init();
+        tma_prefetch_desc(&p.tmY);
+    }
+    if (warp == TCS_W_MMA) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *reinterpret_cast<const unsigned *>(cbg + 128);
+    if (warp < 4) {
+        // the A operand: this thread's query (TMEM lane 32 warp + lane), 4 planes x d bytes
+        const unsigned q = q0 + 32u * warp + lane;
+        const unsigned tq = tmem + ((32u * warp) << 16) + 256u;
+        for (unsigned kc = 0; kc < KC; kc++)
+            for (unsigned c16 = 0; c16 < 8; c16++) {
+                uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                if (q < p.Q) u = *reinterpret_cast<const uint4 *>(p.ub8 + (size_t)q * p.d + 128u * kc + 16u * c16);
+#pragma unroll
+                for (unsigned pl = 0; pl < 4; pl++) {
+                    const unsigned w4[4] = {query_plane_word(u.x, pl), query_plane_word(u.y, pl), query_plane_word(u.z, pl), query_plane_word(u.w, pl)};
+                    tmem_st4(tq + (kc * 4u + pl) * 32u + 4u * c16, w4);
+                }
+            }
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned long long n_tiles = (p.S_local + 127ull) / 128ull;
+
+    if (warp == TCS_W_PROD) {
+        if (lane == 0) {
+            unsigned it = 0;
+            SCK_DECL
+            for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (unsigned kc = 0; kc < KC; kc++, it++) {
+                    const unsigned s = it % TCS_NY, ph = (it / TCS_NY) & 1u;
+                    SCK(1);
+                    mbar_wait(bar_yfree + 8 * s, ph ^ 1u);
+                    SCK(0);
+                    mbar_expect_tx(bar_yfull + 8 * s, TCS_TILE);
+                    tma_load_2d(yrg + s * TCS_TILE, &p.tmY, (int)(128u * kc), (int)(tile * 128ull), bar_yfull + 8 * s);
+                }
+            SCK(1); SCK_FLUSH(0);
+        }
+    } else if (warp == TCS_W_MMA) {
+        if (lane == 0) {
+            const unsigned idesc = umma_idesc_i8(TQ_QB, 128);
+            unsigned it = 0, tc = 0;
+            const unsigned long long ydesc0 = umma_desc_sw128(yrg), pdesc0 = umma_desc_sw128(prg);
+            SCK_DECL
+            for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tc++) {
+                const unsigned buf = tc & 1u;
+                SCK(2);
+                mbar_wait(bar_dfree + 8 * buf, ((tc >> 1) & 1u) ^ 1u);
+                SCK(0);
+                tc_fence_after();
+                for (unsigned kc = 0; kc < KC; kc++, it++) {
+                    const unsigned ys = it % TCS_NY, ps = it % TQ_NP, php = (it / TQ_NP) & 1u;
+                    SCK(2);
+                    mbar_wait(bar_built + 8 * ps, php);                     // implies the Y tile has arrived (the builders read it)
+                    SCK(1);
+                    tc_fence_after();
+#pragma unroll
+                    for (unsigned pl = 0; pl < 4; pl++) {
+                        const unsigned long long bd = pl == 0 ? ydesc0 + (unsigned long long)(ys * (TCS_TILE >> 4))
+                                                              : pdesc0 + (unsigned long long)((ps * 3u + pl - 1u) * (TCS_TILE >> 4));
+                        const unsigned at = tmem + 256u + (kc * 4u + pl) * 32u;
+#pragma unroll
+                        for (unsigned j = 0; j < 4; j++) umma_i8_ts(tmem + buf * 128u, at + 8u * j, bd + 2ull * j, idesc, (kc | pl | j) ? 1u : 0u);
+                    }
+                    umma_commit(bar_yfree + 8 * ys);
+                    umma_commit(bar_pfree + 8 * ps);
+                }
+                umma_commit(bar_dfull + 8 * buf);
+            }
+            SCK(2); SCK_FLUSH(1);
+        }
+    } else if (warp < TCS_BUILDERS) {
+        const unsigned bt = threadIdx.x;                                   // 0 .. 255
+        unsigned it = 0;
+        SCK_DECL
+        for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (unsigned kc = 0; kc < KC; kc++, it++) {
+                const unsigned ys = it % TCS_NY, phy = (it / TCS_NY) & 1u, ps = it % TQ_NP, php = (it / TQ_NP) & 1u;
+                SCK(1);
+                mbar_wait(bar_pfree + 8 * ps, php ^ 1u);                   // the MMAs that read this plane buffer have completed
+                SCK(2);
+                mbar_wait(bar_yfull + 8 * ys, phy);
+                SCK(0);
+                const unsigned char *y0 = gbase + (yrg - sbase) + (size_t)ys * TCS_TILE;
+                unsigned char *p0 = gbase + (prg - sbase) + (size_t)ps * 3u * TCS_TILE;
+#pragma unroll
+                for (unsigned i = 0; i < TCS_TILE / 16u / (TCS_BUILDERS * 32u); i++) {
+                    const unsigned off = 16u * (bt + i * TCS_BUILDERS * 32u);
+                    const uint4 y = *reinterpret_cast<const uint4 *>(y0 + off);
+                    uint4 i1, i2, i3;
+                    indicator_planes(y.x, i1.x, i2.x, i3.x);
+                    indicator_planes(y.y, i1.y, i2.y, i3.y);
+                    indicator_planes(y.z, i1.z, i2.z, i3.z);
+                    indicator_planes(y.w, i1.w, i2.w, i3.w);
+                    *reinterpret_cast<uint4 *>(p0 + off) = i1;
+                    *reinterpret_cast<uint4 *>(p0 + TCS_TILE + off) = i2;
+                    *reinterpret_cast<uint4 *>(p0 + 2u * TCS_TILE + off) = i3;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_built + 8 * ps);
+            }
+        SCK(1);
+        if (warp == TCS_W_BUILD) SCK_FLUSH(2);
+    } else {
+        // epilogue warps: warp w reads TMEM lanes 32 (w % 4) .. + 31 = queries q0 + 32 (w % 4) + lane; the two warps of a quadrant take
+        // accumulator columns (slots of the tile) 0-63 and 64-127, in chunks of 32
+        const int la = p.la;
+        const unsigned sat_lim = 4u * (unsigned)la + 3u;
+        const unsigned ew = warp - TCS_W_EPI;
+        const unsigned quad = warp & 3u, half = ew >> 2;
+        const unsigned tq = tmem + ((32u * quad) << 16);
+        const unsigned ql = 32u * quad + lane;
+        const bool qok = q0 + ql < p.Q;
+        const unsigned umax_q = umax_s[ql];
+        unsigned umax_all = 0;
+        for (unsigned i = 0; i < TQ_QB; i++) umax_all = max(umax_all, umax_s[i]);
+        unsigned char *brow = p.bins + (size_t)(q0 + ql) * p.S_local;
+        const signed char *urow = p.ub8 + (size_t)(q0 + 32u * quad) * p.d;   // + src * d
+        const bool al16 = (p.S_local % 16ull) == 0ull;
+        unsigned tc = 0;
+        // row maxima of the 64 slots of this half: lane holds slots lane and 32 + lane, loaded one tile ahead
+        unsigned rm_next[2] = {0u, 0u};
+        SCK_DECL
+        {
+            const unsigned long long r0 = (unsigned long long)blockIdx.x * 128ull + 64u * half + lane;
+            if (blockIdx.x < n_tiles) {
+                if (r0 < p.S_local) rm_next[0] = (unsigned)p.rowmax[r0];
+                if (r0 + 32u < p.S_local) rm_next[1] = (unsigned)p.rowmax[r0 + 32u];
+            }
+        }
+        for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tc++) {
+            const unsigned buf = tc & 1u;
+            const unsigned long long slot0 = tile * 128ull + 64u * half;         // first slot of this warp's columns
+            const unsigned rm[2] = {rm_next[0], rm_next[1]};
+            {
+                const unsigned long long rn = slot0 + (unsigned long long)gridDim.x * 128ull + lane;
+                const bool more = tile + gridDim.x < n_tiles;
+                rm_next[0] = (more && rn < p.S_local) ? (unsigned)p.rowmax[rn] : 0u;
+                rm_next[1] = (more && rn + 32u < p.S_local) ? (unsigned)p.rowmax[rn + 32u] : 0u;
+            }
+            const unsigned nvalid = (slot0 >= p.S_local) ? 0u : (unsigned)min(64ull, p.S_local - slot0);
+            SCK(3);
+            mbar_wait(bar_dfull + 8 * buf, (tc >> 1) & 1u);
+            SCK(0);
+            tc_fence_after();
+#pragma unroll
+            for (unsigned c = 0; c < 2; c++) {
+                unsigned v[32];
+                {
+                    unsigned v0[16], v1[16];
+                    tmem_ld16(tq + buf * 128u + 64u * half + 32u * c, v0);
+                    tmem_ld16(tq + buf * 128u + 64u * half + 32u * c + 16u, v1);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) { v[i] = v0[i]; v[16 + i] = v1[i]; }
+                }
+                if (c == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_dfree + 8 * buf);          // the accumulators are in registers: the tile is free
+                }
+                SCK(1);
+                // (slot, query) pairs with a product that may saturate: the reference order of operations, product by product, by
+                // the whole warp; the exact sum replaces the accumulator (times 4: the accumulators are 4 x the score)
+                unsigned risky_slots = __ballot_sync(0xffffffffu, rm[c] * umax_all > sat_lim);
+                while (risky_slots) {
+                    const unsigned sidx = (unsigned)(__ffs((int)risky_slots) - 1);
+                    risky_slots &= risky_slots - 1u;
+                    const unsigned rms = __shfl_sync(0xffffffffu, rm[c], (int)sidx);
+                    const bool mine = qok && rms * umax_q > sat_lim;
+                    unsigned lm = __ballot_sync(0xffffffffu, mine);
+                    const signed char *yr = p.Y + (slot0 + 32u * c + sidx) * p.d;
+                    unsigned val = 0u;
+                    while (lm) {
+                        const unsigned src = (unsigned)(__ffs((int)lm) - 1);
+                        lm &= lm - 1u;
+                        const signed char *ur = urow + (size_t)src * p.d;
+                        int sp = 0;
+                        for (unsigned t0 = 8u * lane; t0 < p.d; t0 += 256u) {
+                            const uint2 yv = *reinterpret_cast<const uint2 *>(yr + t0), uv = *reinterpret_cast<const uint2 *>(ur + t0);
+#pragma unroll
+                            for (int b8 = 0; b8 < 4; b8++) {
+                                sp += qi_mul((int)(signed char)((yv.x >> (8 * b8)) & 0xFFu), (int)(signed char)((uv.x >> (8 * b8)) & 0xFFu), la, p.fb);
+                                sp += qi_mul((int)(signed char)((yv.y >> (8 * b8)) & 0xFFu), (int)(signed char)((uv.y >> (8 * b8)) & 0xFFu), la, p.fb);
+                            }
+                        }
+                        sp = __reduce_add_sync(0xffffffffu, sp);
+                        if (lane == src) val = (unsigned)(qi_clamp(sp, la) * 4);
+                    }
+#pragma unroll
+                    for (unsigned i = 0; i < 32; i++)
+                        if (i == sidx && mine) v[i] = val;
+                }
+                SCK(2);
+                // bins of 32 slots: 32 contiguous bytes of this query's row
+                const unsigned nv = (nvalid > 32u * c) ? min(32u, nvalid - 32u * c) : 0u;
+                unsigned w8[8];
+#pragma unroll
+                for (unsigned i = 0; i < 32; i++) {
+                    const unsigned code = (unsigned)(qi_clamp((int)v[i] >> 2, la) + (int)p.bias);      // exact: a multiple of 4
+                    if ((i & 3u) == 0u) w8[i >> 2] = code; else w8[i >> 2] |= code << (8u * (i & 3u));
+                }
+                if (qok) {
+                    unsigned char *dst = brow + slot0 + 32u * c;
+                    if (al16 && nv == 32u) {
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                        *reinterpret_cast<uint4 *>(dst + 16) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+                    } else {
+#pragma unroll
+                        for (unsigned i = 0; i < 32; i++)
+                            if (i < nv) dst[i] = (unsigned char)((w8[i >> 2] >> (8u * (i & 3u))) & 0xFFu);
+                    }
+                }
+                SCK(3);
+            }
+        }
+        if (ew == 0) SCK_FLUSH(3);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == TCS_W_MMA) tmem_dealloc(tmem, 512);
+}
+
 // Query planes of k_big_scores_tc as the shared-memory image of its B operand: for query block qb, K chunk kc, plane pl: 64 rows
 // (queries) x 128 bytes with the 16-byte chunks XOR-swizzled by (row & 7) (the 128-byte swizzle of the K-major descriptor).
 // Plane 0 = Q_bin(u); planes a = 1..3 = -sgn(u) ((a (|u| & 3)) & 3) (negated: all four contractions accumulate into one tile).
@@ -1025,6 +1324,104 @@ __global__ void __launch_bounds__(256) k_big_hist(const BinT *__restrict__ bins,
         __syncthreads();
         for (unsigned i = threadIdx.x; i < NB; i += blockDim.x)
             if (hs[i]) atomicAdd(&hq[i], hs[i]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_big_hist_lanes (byte bins): the same histogram without atomics in the inner loop.  A warp takes (query, run of slots) tasks;
+// every LANE keeps its own 16-bit counter per bin in shared memory ([bin][lane], 16 KB per warp), so an update is a plain
+// load-add-store of an address no other thread touches.  Four bins are handled together: the four counters are loaded first, a
+// later value of the group that repeats an earlier bin takes the earlier result, the stores follow in order -- the dependent
+// load -> add -> store chain is paid once per four values.  At the end of a task the 32 lane copies of every bin are summed
+// (one warp reduction per bin) and added to the global histogram.  k_big_hist's shared-memory atomics cost ~7 cycles per warp
+// instruction; this form is bounded by plain shared-memory traffic.
+// -------------------------------------------------------------------------------------------------
+constexpr unsigned HL_WARPS = 12;
+
+// (a bank-conflict-free counter layout -- the two bins of a pair in the lane's own 32-bit word -- was measured 15 % slower: the
+// kernel is bound by instruction issue, and that layout costs two more integer instructions per value)
+__device__ __forceinline__ void hl_count4(unsigned w, unsigned short *cl)
+{
+    const unsigned c0 = w & 0xFFu, c1 = (w >> 8) & 0xFFu, c2 = (w >> 16) & 0xFFu, c3 = w >> 24;
+    unsigned short *a0 = cl + c0 * 32u, *a1 = cl + c1 * 32u, *a2 = cl + c2 * 32u, *a3 = cl + c3 * 32u;
+    unsigned n0 = *a0, n1 = *a1, n2 = *a2, n3 = *a3;
+    n0 += 1u;
+    n1 = ((c1 == c0) ? n0 : n1) + 1u;
+    n2 = ((c2 == c1) ? n1 : ((c2 == c0) ? n0 : n2)) + 1u;
+    n3 = ((c3 == c2) ? n2 : ((c3 == c1) ? n1 : ((c3 == c0) ? n0 : n3))) + 1u;
+    *a0 = (unsigned short)n0;
+    *a1 = (unsigned short)n1;
+    *a2 = (unsigned short)n2;
+    *a3 = (unsigned short)n3;
+}
+
+__global__ void __launch_bounds__(HL_WARPS * 32, 1) k_big_hist_lanes(const unsigned char *__restrict__ bins, unsigned long long S_local, unsigned Q, unsigned NB,
+                                                                     unsigned chunk, unsigned *__restrict__ hist)
+{
+    extern __shared__ __align__(16) unsigned char hsm[];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned short *cnt = reinterpret_cast<unsigned short *>(hsm) + (size_t)warp * (256u * 32u);      // [bin][lane]
+    for (unsigned i = lane; i < 256u * 32u / 2u; i += 32) reinterpret_cast<unsigned *>(cnt)[i] = 0u;
+    __syncwarp();
+    unsigned short *cl = cnt + lane;
+    const unsigned long long nch = (S_local + chunk - 1) / chunk, ntask = nch * Q;       // chunk: a multiple of 16, at most 2^20 (16-bit counters)
+    const bool vec = (S_local % 16ull) == 0ull && (reinterpret_cast<uintptr_t>(bins) & 15) == 0;
+    for (unsigned long long task = (unsigned long long)blockIdx.x * HL_WARPS + warp; task < ntask; task += (unsigned long long)gridDim.x * HL_WARPS) {
+        const unsigned q = (unsigned)(task / nch);
+        const unsigned long long s0 = (task % nch) * chunk, s1 = min(S_local, s0 + (unsigned long long)chunk);
+        const unsigned char *b = bins + (size_t)q * S_local;
+        const unsigned nvec = vec ? (unsigned)((s1 - s0) / 16ull) : 0u;
+        const uint4 *vb = reinterpret_cast<const uint4 *>(b + s0);
+        // groups of 128 vectors (four per lane), the next group's loads issued before the current one is counted: eight 128-bit
+        // loads in flight per lane
+        const unsigned ngrp = nvec / 128u;
+        uint4 cur[4], nxt[4];
+#pragma unroll
+        for (unsigned k = 0; k < 4; k++) {
+            cur[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (ngrp) cur[k] = __ldg(vb + lane + 32u * k);
+        }
+        for (unsigned g = 0; g < ngrp; g++) {
+#pragma unroll
+            for (unsigned k = 0; k < 4; k++) {
+                nxt[k] = make_uint4(0u, 0u, 0u, 0u);
+                if (g + 1u < ngrp) nxt[k] = __ldg(vb + (size_t)(g + 1u) * 128u + lane + 32u * k);
+            }
+#pragma unroll
+            for (unsigned k = 0; k < 4; k++) {
+                hl_count4(cur[k].x, cl);
+                hl_count4(cur[k].y, cl);
+                hl_count4(cur[k].z, cl);
+                hl_count4(cur[k].w, cl);
+            }
+#pragma unroll
+            for (unsigned k = 0; k < 4; k++) cur[k] = nxt[k];
+        }
+        for (unsigned i = ngrp * 128u + lane; i < nvec; i += 32) {
+            const uint4 v = __ldg(vb + i);
+            hl_count4(v.x, cl);
+            hl_count4(v.y, cl);
+            hl_count4(v.z, cl);
+            hl_count4(v.w, cl);
+        }
+        for (unsigned long long s = s0 + 16ull * nvec + lane; s < s1; s += 32) cl[(unsigned)b[s] * 32u] += 1;
+        __syncwarp();
+        unsigned *hq = hist + (size_t)q * NB;
+        for (unsigned bin0 = 0; bin0 < NB; bin0 += 8) {
+            unsigned c[8], mine = 0u;
+#pragma unroll
+            for (unsigned k = 0; k < 8; k++) {                  // cnt has 256 rows: bins NB .. 255 stay zero
+                c[k] = cl[(bin0 + k) * 32u];
+                cl[(bin0 + k) * 32u] = 0;
+            }
+#pragma unroll
+            for (unsigned k = 0; k < 8; k++) {
+                const unsigned t = __reduce_add_sync(0xffffffffu, c[k]);
+                if (lane == k) mine = t;
+            }
+            if (lane < 8u && bin0 + lane < NB && mine) atomicAdd(hq + bin0 + lane, mine);
+        }
+        __syncwarp();
     }
 }
 
@@ -1145,13 +1542,25 @@ __global__ void __launch_bounds__(256) k_big_read(const ReadParams p)
     const unsigned long long n_iter = (n_items + stride - 1) / stride;
     // byte compare v >= thr on four packed bytes: high bit of ((v & 0x7F) + K) combined with the byte's own high bit
     const unsigned K = (thr <= 128u) ? (128u - thr) * 0x01010101u : (256u - thr) * 0x01010101u;
-    for (unsigned long long it = 0; it < n_iter; it++) {
-        const unsigned long long i = it * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // four 128-bit loads per thread are issued before the first is examined (the scan is a pure stream: a thread with one load in
+    // flight per iteration left the kernel latency-bound at 2.7 TB/s)
+    for (unsigned long long it0 = 0; it0 < n_iter; it0 += 4) {
+      uint4 pre[4];
+#pragma unroll
+      for (unsigned u = 0; u < 4; u++) {
+          const unsigned long long i = (it0 + u) * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+          pre[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (vec && it0 + u < n_iter && i < n_items) pre[u] = __ldg(reinterpret_cast<const uint4 *>(b) + i);
+      }
+#pragma unroll
+      for (unsigned u = 0; u < 4; u++) {
+        if (it0 + u >= n_iter) break;                         // block-uniform
+        const unsigned long long i = (it0 + u) * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
         unsigned w[4] = {0u, 0u, 0u, 0u};
         unsigned hitmask = 0;                                 // bit k: bin k of this item is selected
         if (i < n_items) {
             if (vec) {
-                const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(b) + i);
+                const uint4 v4 = pre[u];
                 w[0] = v4.x; w[1] = v4.y; w[2] = v4.z; w[3] = v4.w;
                 bool maybe = true;
                 if (sizeof(BinT) == 1) {
@@ -1199,6 +1608,7 @@ __global__ void __launch_bounds__(256) k_big_read(const ReadParams p)
                 if (p.nsel && lane == 0) atomicAdd(&p.nsel[q], 1u);
             }
         }
+      }
     }
 }
 
@@ -1348,6 +1758,7 @@ struct qmann_bigmem {
     // k_big_scores_tc (tcgen05): query planes as the B operand's shared-memory image, one tensor map of Y per hop
     uint4 *bplanes;
     bool tc_ok;
+    bool tq_ok;                 // k_big_scores_tq: queries in tensor memory, 128 per pass, histogram fused (d <= 256, byte bins)
     CUtensorMap tmY[MAXH];
     // k_big_scores_fast inputs per hop: Y = Q_att(M) (== M when the re-quantisation is the identity), row maxima
     const signed char *Y[MAXH];
@@ -1572,6 +1983,9 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
             if (b->fast[h]) ok = tmap_bytes_rows(&b->tmY[h], b->Y[h], S_local, c.d);
         if (ok) BCUDA_B(cudaMalloc((void **)&b->bplanes, (size_t)((Q_max + TCS_QB - 1) / TCS_QB) * (c.d / 128) * 4 * 8192));
         b->tc_ok = ok;
+        const char *env_tq = getenv("QMANN_BIGMEM_TQ");
+        const size_t need_tq = (size_t)(TCS_NY + 3 * TQ_NP) * TCS_TILE + 2048;
+        b->tq_ok = ok && c.d <= 256 && b->bin8 && c.mode == 2 && b->NB <= 256 && need_tq <= (size_t)b->smem_optin && !(env_tq && atoi(env_tq) == 0);
     }
     BCUDA_B(cudaDeviceSynchronize());
     *out = b;
@@ -1622,7 +2036,30 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
         int rc;
         const bool prof = b->profile && b->pused + 2 <= 2 * MAXH;
         if (prof) BCUDA(cudaEventRecord(b->pev[b->pused], st));
-        if (b->fast[h] && b->tc_ok && Q >= 4) {
+        bool hist_done = false;
+        if (b->fast[h] && b->tq_ok && Q >= 4) {
+            TqScoreParams tp;
+            tp.tmY = b->tmY[h];
+            tp.Y = b->Y[h]; tp.rowmax = b->rowmax[h]; tp.S_local = b->S_local; tp.d = d; tp.Q = Q; tp.la = f.la; tp.fb = f.fb;
+            tp.ub8 = b->ub8; tp.umax = b->umax; tp.bins = reinterpret_cast<unsigned char *>(b->bins); tp.bias = (unsigned)f.la;
+            tp.clk = nullptr;
+#ifdef QMANN_TC_TRACE
+            static unsigned long long *clk_host_q = nullptr;
+            if (!clk_host_q) BCUDA(cudaHostAlloc((void **)&clk_host_q, 16 * 8, cudaHostAllocMapped));
+            { unsigned long long *dp = nullptr; BCUDA(cudaHostGetDevicePointer((void **)&dp, clk_host_q, 0)); tp.clk = dp; }
+            g_tcs_clk = clk_host_q;
+#endif
+            const size_t smem = (size_t)(TCS_NY + 3 * TQ_NP) * TCS_TILE + 2048;
+            static bool attr_done = false;
+            if (!attr_done) { BCUDA(cudaFuncSetAttribute(k_big_scores_tq, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_optin)); attr_done = true; }
+            const unsigned long long tiles = (b->S_local + 127) / 128;
+            const unsigned gx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(tiles, (unsigned long long)b->sm_count));
+            k_big_scores_tq<<<dim3(gx, (Q + TQ_QB - 1) / TQ_QB), TCS_WARPS * 32, smem, st>>>(tp);
+            count_launch();
+            BCUDA(cudaPeekAtLastError());
+            rc = QMANN_OK;
+        }
+        else if (b->fast[h] && b->tc_ok && Q >= 4) {
             const unsigned qblocks = (Q + TCS_QB - 1) / TCS_QB, KC = d / 128;
             k_big_prep_bplanes<<<std::min(512u, (qblocks * KC * 2048u + 255u) / 256u), 256, 0, st>>>(b->ub8, Q, d, b->bplanes);
             count_launch();
@@ -1678,10 +2115,25 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
         else rc = (Q >= 16) ? launch_scores<2, 16>(b, sp, st) : (Q >= 4 ? launch_scores<2, 4>(b, sp, st) : launch_scores<2, 1>(b, sp, st));
         if (rc) return rc;
         if (prof) { BCUDA(cudaEventRecord(b->pev[b->pused + 1], st)); b->pused += 2; }
+        if (hist_done) return QMANN_OK;
         // mode 2 bins are code + la of THIS hop; the histogram is indexed with the common bias
         const int use_smem = b->NB <= 8192;
         const unsigned gx = (unsigned)std::min<unsigned long long>((b->S_local + 255) / 256, (unsigned long long)b->sm_count * 4);
-        if (b->bin8) k_big_hist<unsigned char><<<dim3(std::max(1u, gx), Q), 256, use_smem ? b->NB * 4 : 0, st>>>(reinterpret_cast<const unsigned char *>(b->bins), b->S_local, b->NB, dev_hist, use_smem);
+        const char *env_hl = getenv("QMANN_BIGMEM_HIST_LANES");          // 0: the shared-memory-atomic kernel (A/B tests)
+        const bool hist_lanes_on = !(env_hl && atoi(env_hl) == 0);
+        const size_t hl_smem = (size_t)HL_WARPS * 256 * 32 * 2;
+        // (small jobs keep k_big_hist: a task's end-of-run reduction over 255 bins x 32 lanes needs ~16 K slots to amortise)
+        if (b->bin8 && b->NB <= 256 && hist_lanes_on && hl_smem <= (size_t)b->smem_optin && (unsigned long long)Q * b->S_local / 16384 >= 2ull * b->sm_count * HL_WARPS) {
+            static bool hl_attr = false;
+            if (!hl_attr) { BCUDA(cudaFuncSetAttribute(k_big_hist_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hl_smem)); hl_attr = true; }
+            // tasks of 2^16 slots (2048 values per lane) when that leaves at least four per warp, else 2^14
+            const unsigned long long nw = (unsigned long long)b->sm_count * HL_WARPS, work = (unsigned long long)Q * b->S_local;
+            const unsigned chunk = (work / 65536 >= 4 * nw) ? 65536u : 16384u;
+            const unsigned long long ntask = ((b->S_local + chunk - 1) / chunk) * Q;
+            const unsigned hgx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((ntask + HL_WARPS - 1) / HL_WARPS, (unsigned long long)b->sm_count));
+            k_big_hist_lanes<<<hgx, HL_WARPS * 32, hl_smem, st>>>(reinterpret_cast<const unsigned char *>(b->bins), b->S_local, Q, b->NB, chunk, dev_hist);
+        }
+        else if (b->bin8) k_big_hist<unsigned char><<<dim3(std::max(1u, gx), Q), 256, use_smem ? b->NB * 4 : 0, st>>>(reinterpret_cast<const unsigned char *>(b->bins), b->S_local, b->NB, dev_hist, use_smem);
         else         k_big_hist<unsigned short><<<dim3(std::max(1u, gx), Q), 256, use_smem ? b->NB * 4 : 0, st>>>(reinterpret_cast<const unsigned short *>(b->bins), b->S_local, b->NB, dev_hist, use_smem);
         count_launch();
         BCUDA(cudaPeekAtLastError());
@@ -1708,7 +2160,8 @@ int qmann_bigmem_hop_read(qmann_bigmem *b, uint32_t h, const uint32_t *dev_hist,
         ReadParams rp;
         rp.bins = b->bins; rp.pq = b->pq; rp.thr = b->thr; rp.C = b->C[h]; rp.S_local = b->S_local; rp.NB = b->NB; rp.d = d; rp.f = f;
         rp.partial = dev_partial; rp.nsel = b->nsel;
-        const unsigned gx = (unsigned)std::min<unsigned long long>((b->S_local / 8 + 255) / 256 + 1, (unsigned long long)b->sm_count * 4);
+        const unsigned long long items = b->S_local / (b->bin8 ? 16 : 8) + 1;                    // 128-bit vectors of bins per query
+        const unsigned gx = (unsigned)std::min<unsigned long long>((items + 1023) / 1024, (unsigned long long)b->sm_count * 4);      // four per thread
         if (b->bin8) k_big_read<unsigned char><<<dim3(std::max(1u, gx), Q), 256, 0, st>>>(rp);
         else         k_big_read<unsigned short><<<dim3(std::max(1u, gx), Q), 256, 0, st>>>(rp);
         count_launch();

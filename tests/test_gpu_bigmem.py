@@ -85,10 +85,12 @@ def test_bigmem_matches_oracle(mode, d, S, Q, iwl, qmann, synth, qmo):
 @pytest.mark.parametrize("d,S,Q,sigma,plant", [(16, 4099, 1, 0.6, 3.0), (32, 3001, 2, 2.0, 3.0), (64, 2050, 5, 0.2, 1.0), (128, 1500, 3, 1.0, 3.0),
                                                  (256, 1111, 4, 0.6, 3.0), (256, 777, 1, 4.0, 3.0), (512, 515, 7, 0.6, 2.0),
                                                  (64, 1999, 64, 0.6, 3.0), (256, 1030, 70, 0.3, 2.0), (128, 523, 9, 3.0, 3.0),
-                                                 (256, 5003, 200, 0.6, 3.0), (128, 130, 64, 1.5, 3.0)])
+                                                 (256, 5003, 200, 0.6, 3.0), (128, 130, 64, 1.5, 3.0),
+                                                 (256, 4224, 130, 0.6, 3.0), (128, 2048, 64, 1.5, 3.0), (256, 70000, 8, 0.6, 3.0)])
 def test_bigmem_fast_scorer_equals_per_product(d, S, Q, sigma, plant, qmann, synth, monkeypatch):
-    """k_big_scores_fast (packed low-bit / dp4a form) and, for Q >= 4, the tensor-core scorers -- k_big_scores_tc (tcgen05.mma
-    kind::i8, TMA-staged tiles, accumulators in tensor memory; d % 128 == 0) and k_big_scores_mma (mma.sync, d % 64 == 0): four int8
+    """k_big_scores_fast (packed low-bit / dp4a form) and, for Q >= 4, the tensor-core scorers -- k_big_scores_tq (tcgen05.mma
+    kind::i8 with the query planes in tensor memory, 128 queries per pass; d = 128 / 256), k_big_scores_tc (query
+    planes in shared memory; d % 128 == 0) and k_big_scores_mma (mma.sync, d % 64 == 0): four int8
     contractions each -- saturating rows recomputed product by product, against the per-product kernel
     k_big_scores on the same memory: identical histograms, controller states and answers.
     sigma = 2..4 makes most rows saturate somewhere (the in-kernel exact path), sigma = 0.2 none."""
@@ -106,6 +108,17 @@ def test_bigmem_fast_scorer_equals_per_product(d, S, Q, sigma, plant, qmann, syn
     many = _run(qmann, cfg, w, M8, C8, u0, shards=3)
     np.testing.assert_array_equal(many["hist"], slow["hist"].astype(np.int64))
     np.testing.assert_array_equal(many["u"], slow["u"])
+    # the histogram above came from k_big_hist_lanes (lane-private counters); now the shared-memory-atomic kernel
+    monkeypatch.setenv("QMANN_BIGMEM_HIST_LANES", "0")
+    atom = _run(qmann, cfg, w, M8, C8, u0)
+    np.testing.assert_array_equal(atom["hist"], slow["hist"], err_msg="k_big_hist")
+    np.testing.assert_array_equal(atom["pred"], slow["pred"])
+    monkeypatch.delenv("QMANN_BIGMEM_HIST_LANES")
+    # d <= 256 took k_big_scores_tq above (queries in tensor memory, 128 per pass); now k_big_scores_tc + k_big_hist
+    monkeypatch.setenv("QMANN_BIGMEM_TQ", "0")
+    tcs = _run(qmann, cfg, w, M8, C8, u0)
+    for k in ("hist", "o", "u", "pred"):
+        np.testing.assert_array_equal(tcs[k], slow[k], err_msg=f"tcgen05 scorer (queries in shared memory): {k}")
     # the mma.sync scorer alone (tcgen05 scorer switched off), then the packed CUDA-core kernel alone
     monkeypatch.setenv("QMANN_BIGMEM_TC", "0")
     mma = _run(qmann, cfg, w, M8, C8, u0)
