@@ -505,15 +505,17 @@ def _bigmem_measure(args, torch, qlib, synth, cfg, weights, mem, u0, Q, W, K, ra
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ((ncu_traffic("k_big_scores_fast") or {}).get("dram_bytes_per_launch") if (world == 1 and Q == 1) else
-                                     (ncu_traffic("k_big_scores_tc") or {}).get("dram_bytes_per_launch") if (world == 1 and Q == 64) else None),
-                         "kernel": "k_big_scores_fast" if Q < 4 else ("k_big_scores_mma" if os.environ.get("QMANN_BIGMEM_TC") == "0" else "k_big_scores_tc"),
+                                     (ncu_traffic("k_big_scores_tq") or {}).get("dram_bytes_per_launch") if (world == 1 and Q == 64) else None),
+                         "kernel": "k_big_scores_fast" if Q < 4 else ("k_big_scores_mma" if os.environ.get("QMANN_BIGMEM_TC") == "0" else
+                                                                      ("k_big_scores_tc" if os.environ.get("QMANN_BIGMEM_TQ") == "0" else "k_big_scores_tq")),
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
                          "algorithmic_bytes_per_launch": bytes_launch, "launch_ms": k_scores_ms,
-                         "note": "one launch streams one hop's M shard (S_local*d int8) for a block of up to 64 queries (Q > 64: one pass per "
-                                 "block); the C rows are a sparse gather of the <= 2^frac slots whose quantised attention weight is non-zero, so "
-                                 "they are not streamed.  Q < 4: k_big_scores_fast, HBM-bound.  Q >= 4: k_big_scores_tc, the truncated products "
-                                 "as four int8 contractions on tcgen05.mma kind::i8 (TMA-staged tiles, accumulators in tensor memory; "
-                                 "4*S*d*Q multiply-adds per hop), bound by the indicator-plane construction and the MMA issue, not by HBM"},
+                         "note": "one launch streams one hop's M shard (S_local*d int8) once per block of up to 128 queries (Q > 128: one pass "
+                                 "per block); the C rows are a sparse gather of the <= 2^frac slots whose quantised attention weight is non-zero, so "
+                                 "they are not streamed.  Q < 4: k_big_scores_fast, HBM-bound.  Q >= 4: k_big_scores_tq, the truncated products "
+                                 "as four int8 contractions on tcgen05.mma kind::i8 (query planes as the A operand in tensor memory, TMA-staged "
+                                 "memory tiles as B, accumulators in tensor memory; 4*S*d*Q multiply-adds per hop), bound by shared-memory "
+                                 "bandwidth (plane construction + operand reads), not by HBM"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

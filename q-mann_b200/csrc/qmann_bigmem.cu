@@ -10,8 +10,10 @@
 //   k_big_scores   streams M_h once (HBM), lane-per-slot, QB queries register-blocked per pass:
 //                  s[r] = Q_att(sum_t Q_att(Q_att(M[r][t]) * Q_bin(u[t])))        layer_cuda.cu:105-141
 //                  or the Hamming/approximate similarity                          layer_cuda.cu:355-541
-//                  -> 16-bit score bins [Q][S_local]
-//   k_big_hist     per-query histogram of the score bins (shared-memory atomics)
+//                  -> score bins [Q][S_local] (bytes in mode 2, 16-bit in mode 3)
+//                  fast forms of the mode-2 scorer: k_big_scores_fast (Q < 4, HBM-bound), k_big_scores_tq / _tc (tcgen05.mma
+//                  kind::i8, query planes in tensor memory / shared memory), k_big_scores_mma (mma.sync)
+//   k_big_hist_lanes / k_big_hist   per-query histogram of the score bins (lane-private counters / shared-memory atomics)
 //        ---- all-reduce(SUM, u32) of the histograms across ranks (NCCL, by the caller) ----
 //   k_big_softmax  every rank rebuilds the SAME max and double-precision total from the global
 //                  histogram in a fixed order (bins ascending, 256 contiguous ranges, range partials
@@ -987,12 +989,14 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tq(const __gri
     __syncthreads();
     tc_fence_after();
     const unsigned tmem = *reinterpret_cast<const unsigned *>(cbg + 128);
-    if (warp < 4) {
-        // the A operand: this thread's query (TMEM lane 32 warp + lane), 4 planes x d bytes
-        const unsigned q = q0 + 32u * warp + lane;
-        const unsigned tq = tmem + ((32u * warp) << 16) + 256u;
+    if (warp < 16) {
+        // the A operand: this thread's query (TMEM lane 32 (warp % 4) + lane), 4 planes x d bytes; the four warps that can reach a
+        // TMEM quadrant split the 16-byte chunks of a K chunk between them
+        const unsigned aq = warp & 3u, part = warp >> 2;
+        const unsigned q = q0 + 32u * aq + lane;
+        const unsigned tq = tmem + ((32u * aq) << 16) + 256u;
         for (unsigned kc = 0; kc < KC; kc++)
-            for (unsigned c16 = 0; c16 < 8; c16++) {
+            for (unsigned c16 = 2u * part; c16 < 2u * part + 2u; c16++) {
                 uint4 u = make_uint4(0u, 0u, 0u, 0u);
                 if (q < p.Q) u = *reinterpret_cast<const uint4 *>(p.ub8 + (size_t)q * p.d + 128u * kc + 16u * c16);
 #pragma unroll
@@ -1663,6 +1667,82 @@ __global__ void __launch_bounds__(256) k_big_update(const UpdateParams p)
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// k_big_update_fast (frac_bin == 2, d % 16 == 0, linear map on): the linear map with the packed identity of k_big_scores_fast --
+// one dp4a and ~12 integer instructions per four products instead of ~8 per product.  A thread owns one (query, output dim):
+// it walks its Hm row and the query (shared memory) as 128-bit vectors.  A 16-dim vector in which some row of the warp may have a
+// saturating product (rowmax(Hm[i]) * max|Q_bin(u)| over the vector > 4 lw + 3) is evaluated product by product from the same registers.  Every rank repeats this kernel for all queries,
+// so on 8 GPUs it was 13 % of a 1024-query step.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_big_update_fast(const UpdateParams p, const signed char *__restrict__ ub8, const unsigned char *__restrict__ hmax)
+{
+    extern __shared__ uint4 us4[];                              // Q_bin(u) of this query, d bytes; then max|u| per 16-byte vector
+    const unsigned q = blockIdx.x, d = p.d, nv = d / 16;
+    unsigned *um_s = reinterpret_cast<unsigned *>(us4 + nv);
+    const HopFmt f = p.f;
+    for (unsigned k = threadIdx.x; k < nv; k += blockDim.x) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(ub8 + (size_t)q * d + 16u * k);
+        us4[k] = v;
+        const unsigned a4 = __vmaxu4(__vmaxu4(__vabs4(v.x), __vabs4(v.y)), __vmaxu4(__vabs4(v.z), __vabs4(v.w)));
+        um_s[k] = max(max(a4 & 0xFFu, (a4 >> 8) & 0xFFu), max((a4 >> 16) & 0xFFu, a4 >> 24));
+    }
+    __syncthreads();
+    const unsigned sat_lim = 4u * (unsigned)f.lw + 3u;
+    const unsigned i = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool valid = i < d;
+    const unsigned ir = valid ? i : d - 1u;
+    const unsigned hm = valid ? (unsigned)hmax[ir] : 0u;
+    const uint4 *hrow = reinterpret_cast<const uint4 *>(p.Hq + (size_t)ir * d);
+    int acc4 = 0;                                               // 4 x the sum of the truncated products
+#pragma unroll 2
+    for (unsigned k = 0; k < nv; k++) {
+        const uint4 hv = __ldg(hrow + k), uv = us4[k];
+        const unsigned yw[4] = {hv.x, hv.y, hv.z, hv.w}, uw[4] = {uv.x, uv.y, uv.z, uv.w};
+        // a product of this vector may saturate for some row of the warp: the reference order of operations for the whole warp (the
+        // exact form is valid for every lane; deciding per warp keeps the branch uniform)
+        if (__any_sync(0xffffffffu, hm * um_s[k] > sat_lim)) {
+            int sp = 0;
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+#pragma unroll
+                for (int b8 = 0; b8 < 4; b8++) sp += qi_mul(sx8(yw[w], b8), sx8(uw[w], b8), f.lw, f.fb);
+            acc4 += 4 * sp;
+        } else {
+            int D = 0;
+            unsigned cs = 0;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                D = __dp4a((int)yw[w], (int)uw[w], D);
+                const unsigned u0 = uw[w] & 0x01010101u;
+                const unsigned t0 = (yw[w] << 1) & (uw[w] & 0x02020202u);
+                const unsigned t1 = (yw[w] & (u0 << 1)) ^ t0;
+                const unsigned bm = (yw[w] & u0) | t1;                            // x mod 4 per byte
+                const unsigned wv = bm + 0x03030303u;                             // 3..6, bit 2 set iff x mod 4 != 0
+                cs += wv & ~(((yw[w] ^ uw[w]) >> 5) & 0x04040404u);               // clear bit 2 where the product is negative
+            }
+            acc4 += D - (int)__dp4a(cs, 0x01010101u, 0u) + 48;
+        }
+    }
+    if (!valid) return;
+    const int g_w = qi_clamp(acc4 >> 2, f.lw);                                    // exact: a multiple of 4
+    const int a_f = qi_requant(g_w, f.fw, f.lf, f.ff);
+    const int o = qi_clamp(p.partial[(size_t)q * d + i], f.lf);
+    p.u_out[(size_t)q * d + i] = (signed char)qi_clamp(a_f + o, f.lf);
+    if (p.dbg_o) p.dbg_o[(size_t)q * d + i] = (signed char)o;
+    if (p.dbg_g) p.dbg_g[(size_t)q * d + i] = (signed char)g_w;
+}
+
+// hmax[i] = max_j |Hq[i][j]|: one warp per row
+__global__ void __launch_bounds__(256) k_big_rowmax_H(const signed char *__restrict__ Hq, unsigned d, unsigned char *__restrict__ hmax)
+{
+    const unsigned row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= d) return;
+    unsigned mx = 0;
+    for (unsigned j = lane; j < d; j += 32) mx = max(mx, (unsigned)abs((int)Hq[(size_t)row * d + j]));
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) hmax[row] = (unsigned char)min(mx, 255u);
+}
+
 __global__ void k_big_quant_H(const float *__restrict__ w, signed char *__restrict__ out, unsigned n, int iwl, int frac)
 {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (signed char)qi_encode(w[i], iwl, frac);
@@ -1737,6 +1817,8 @@ struct qmann_bigmem {
     unsigned Q_max, Q, NB, bias;
     HopFmt f[MAXH];
     signed char *dev_H[MAXH];
+    unsigned char *dev_hmax[MAXH];      // row maxima of dev_H (k_big_update_fast)
+    bool fast_update;
     const float *dev_W;
     // work buffers
     signed char *u_a, *u_b;          // ping-pong [Q_max][d]
@@ -1938,6 +2020,8 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
         if (!c.lin_map) continue;
         BCUDA_B(cudaMalloc((void **)&b->dev_H[h], (size_t)c.d * c.d));
         k_big_quant_H<<<64, 256>>>(w->dev_Hm[h], b->dev_H[h], c.d * c.d, c.iwl_w[h], c.frac_w[h]);
+        BCUDA_B(cudaMalloc((void **)&b->dev_hmax[h], c.d));
+        k_big_rowmax_H<<<(c.d + 7) / 8, 256>>>(b->dev_H[h], c.d, b->dev_hmax[h]);
         count_launch();
     }
     // k_big_scores_fast (mode 2, two fractional bits in the query format, d/16 a power of two): one pass over each
@@ -1947,6 +2031,7 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
     const char *env_fast = getenv("QMANN_BIGMEM_FAST");
     const bool want_fast = c.mode == 2 && c.frac_bin == 2 && (c16 & (c16 - 1)) == 0 && c16 <= 32 && S_local > 0 &&
                            !(env_fast && atoi(env_fast) == 0);
+    b->fast_update = c.mode == 2 && c.frac_bin == 2 && c.d % 16 == 0 && c.lin_map && !(env_fast && atoi(env_fast) == 0);
     if (want_fast) {
         unsigned *dev_flag = nullptr;
         BCUDA_B(cudaMalloc((void **)&dev_flag, 4));
@@ -2001,7 +2086,7 @@ void qmann_bigmem_destroy(qmann_bigmem *b)
     if (b->gexec) cudaGraphExecDestroy(b->gexec);
     for (int h = 0; h < MAXH; h++) { cudaFree(b->Y_own[h]); cudaFree(b->rowmax[h]); }
     cudaFree(b->pq); cudaFree(b->thr); cudaFree(b->nsel); cudaFree(b->zbuf);
-    for (int h = 0; h < MAXH; h++) cudaFree(b->dev_H[h]);
+    for (int h = 0; h < MAXH; h++) { cudaFree(b->dev_H[h]); cudaFree(b->dev_hmax[h]); }
     if (b->pev[0]) for (int i = 0; i < 2 * MAXH; i++) cudaEventDestroy(b->pev[i]);
     delete b;
 }
@@ -2177,7 +2262,10 @@ int qmann_bigmem_hop_update(qmann_bigmem *b, uint32_t h, const int32_t *dev_part
     UpdateParams up;
     up.partial = dev_partial; up.u_in = b->u_a; up.u_out = b->u_b; up.ub = b->ub; up.Hq = b->cfg.lin_map ? b->dev_H[h] : nullptr;
     up.d = b->cfg.d; up.fu = b->fu; up.f = b->f[h]; up.dbg_o = dev_o; up.dbg_g = dev_g;
-    k_big_update<<<dim3(b->Q, (b->cfg.d + 7) / 8), 256, (size_t)b->cfg.d * 4, (cudaStream_t)stream>>>(up);
+    if (b->fast_update && up.Hq)       // ub8 / umax are those of this hop's k_big_prep_query (mode 2: the same Q_bin(u) feeds scorer and map)
+        k_big_update_fast<<<dim3(b->Q, (b->cfg.d + 255) / 256), 256, (size_t)b->cfg.d + (size_t)(b->cfg.d / 16) * 4, (cudaStream_t)stream>>>(up, b->ub8, b->dev_hmax[h]);
+    else
+        k_big_update<<<dim3(b->Q, (b->cfg.d + 7) / 8), 256, (size_t)b->cfg.d * 4, (cudaStream_t)stream>>>(up);
     count_launch();
     BCUDA(cudaPeekAtLastError());
     std::swap(b->u_a, b->u_b);
