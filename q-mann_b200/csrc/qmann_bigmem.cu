@@ -924,7 +924,7 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tc(const __gri
 // shared-memory atomic hits its own address, ~12 cycles per warp instruction, 6.4 k cycles per tile against 3.1 k of MMA issue;
 // lane-exclusive counters without atomics need one epilogue warp per quadrant, whose dependent load-add-store chains took 9 k.)
 // -------------------------------------------------------------------------------------------------
-constexpr unsigned TQ_QB = 128, TQ_NP = 3;
+constexpr unsigned TQ_QB = 128;
 
 struct TqScoreParams {
     alignas(64) CUtensorMap tmY;     // Y as bytes [S_local][d], box 128 x 128, 128-byte swizzle
@@ -937,6 +937,7 @@ struct TqScoreParams {
     const unsigned *umax;
     unsigned char *bins;
     unsigned bias;
+    unsigned qblk0;                  // first query block of this launch (blockIdx.y counts from it)
     unsigned long long *clk;         // QMANN_TC_TRACE builds: per-role cycle accumulators of CTA (0, 0)
 };
 
@@ -962,6 +963,8 @@ __device__ __forceinline__ unsigned query_plane_word(unsigned uw, unsigned pl)
     return (fill & m) | (~fill & __vneg4(m));
 }
 
+// TQ_NP: depth of the plane ring (3; 2 when the histogram kernel has to fit next to this CTA, see qmann_bigmem_hop_scores)
+template <unsigned TQ_NP>
 __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tq(const __grid_constant__ TqScoreParams p)
 {
     using namespace qtc;
@@ -975,7 +978,7 @@ __global__ void __launch_bounds__(TCS_WARPS * 32, 1) k_big_scores_tq(const __gri
     unsigned char *cbg = gbase + (cb - sbase);
     const unsigned bar_yfull = cb, bar_yfree = cb + 24, bar_built = cb + 48, bar_pfree = cb + 72, bar_dfull = cb + 96, bar_dfree = cb + 112, tmem_slot = cb + 128;
     unsigned *umax_s = reinterpret_cast<unsigned *>(cbg + 256);        // [128]
-    const unsigned q0 = blockIdx.y * TQ_QB;
+    const unsigned q0 = (p.qblk0 + blockIdx.y) * TQ_QB;
     for (unsigned i = threadIdx.x; i < TQ_QB; i += blockDim.x) umax_s[i] = (q0 + i < p.Q) ? p.umax[q0 + i] : 0u;
     if (threadIdx.x == 0) {
         for (unsigned s = 0; s < TCS_NY; s++) { mbar_init(bar_yfull + 8 * s, 1); mbar_init(bar_yfree + 8 * s, 1); }
@@ -1370,7 +1373,8 @@ __global__ void __launch_bounds__(HL_WARPS * 32, 1) k_big_hist_lanes(const unsig
     unsigned short *cl = cnt + lane;
     const unsigned long long nch = (S_local + chunk - 1) / chunk, ntask = nch * Q;       // chunk: a multiple of 16, at most 2^20 (16-bit counters)
     const bool vec = (S_local % 16ull) == 0ull && (reinterpret_cast<uintptr_t>(bins) & 15) == 0;
-    for (unsigned long long task = (unsigned long long)blockIdx.x * HL_WARPS + warp; task < ntask; task += (unsigned long long)gridDim.x * HL_WARPS) {
+    const unsigned nwarps = blockDim.x >> 5;                     // 12, or 5 when the CTA shares the SM with the scorer
+    for (unsigned long long task = (unsigned long long)blockIdx.x * nwarps + warp; task < ntask; task += (unsigned long long)gridDim.x * nwarps) {
         const unsigned q = (unsigned)(task / nch);
         const unsigned long long s0 = (task % nch) * chunk, s1 = min(S_local, s0 + (unsigned long long)chunk);
         const unsigned char *b = bins + (size_t)q * S_local;
@@ -1840,6 +1844,9 @@ struct qmann_bigmem {
     // k_big_scores_tc (tcgen05): query planes as the B operand's shared-memory image, one tensor map of Y per hop
     uint4 *bplanes;
     bool tc_ok;
+    cudaStream_t s2;            // histogram of query block b under the scorer of block b + 1 (qmann_bigmem_hop_scores)
+    cudaEvent_t ev_blk, ev_join;
+    int overlap;                // QMANN_BIGMEM_OVERLAP: 0 off (default), 1 large shards, 2 always
     bool tq_ok;                 // k_big_scores_tq: queries in tensor memory, 128 per pass, histogram fused (d <= 256, byte bins)
     CUtensorMap tmY[MAXH];
     // k_big_scores_fast inputs per hop: Y = Q_att(M) (== M when the re-quantisation is the identity), row maxima
@@ -2069,8 +2076,17 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
         if (ok) BCUDA_B(cudaMalloc((void **)&b->bplanes, (size_t)((Q_max + TCS_QB - 1) / TCS_QB) * (c.d / 128) * 4 * 8192));
         b->tc_ok = ok;
         const char *env_tq = getenv("QMANN_BIGMEM_TQ");
-        const size_t need_tq = (size_t)(TCS_NY + 3 * TQ_NP) * TCS_TILE + 2048;
+        const size_t need_tq = (size_t)(TCS_NY + 3 * 3) * TCS_TILE + 2048;
         b->tq_ok = ok && c.d <= 256 && b->bin8 && c.mode == 2 && b->NB <= 256 && need_tq <= (size_t)b->smem_optin && !(env_tq && atoi(env_tq) == 0);
+    }
+    {
+        const char *env_ov = getenv("QMANN_BIGMEM_OVERLAP");
+        b->overlap = env_ov ? atoi(env_ov) : 0;          // opt-in: measured slower (see qmann_bigmem_hop_scores)
+        if (b->overlap && b->tq_ok) {
+            BCUDA_B(cudaStreamCreateWithFlags(&b->s2, cudaStreamNonBlocking));
+            BCUDA_B(cudaEventCreateWithFlags(&b->ev_blk, cudaEventDisableTiming));
+            BCUDA_B(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+        }
     }
     BCUDA_B(cudaDeviceSynchronize());
     *out = b;
@@ -2084,6 +2100,9 @@ void qmann_bigmem_destroy(qmann_bigmem *b)
     cudaFree(b->ub8); cudaFree(b->umax); cudaFree(b->bfrag); cudaFree(b->bplanes);
     cudaFree(b->xhist); cudaFree(b->xpartial);
     if (b->gexec) cudaGraphExecDestroy(b->gexec);
+    if (b->ev_blk) cudaEventDestroy(b->ev_blk);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
+    if (b->s2) cudaStreamDestroy(b->s2);
     for (int h = 0; h < MAXH; h++) { cudaFree(b->Y_own[h]); cudaFree(b->rowmax[h]); }
     cudaFree(b->pq); cudaFree(b->thr); cudaFree(b->nsel); cudaFree(b->zbuf);
     for (int h = 0; h < MAXH; h++) { cudaFree(b->dev_H[h]); cudaFree(b->dev_hmax[h]); }
@@ -2126,7 +2145,7 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
             TqScoreParams tp;
             tp.tmY = b->tmY[h];
             tp.Y = b->Y[h]; tp.rowmax = b->rowmax[h]; tp.S_local = b->S_local; tp.d = d; tp.Q = Q; tp.la = f.la; tp.fb = f.fb;
-            tp.ub8 = b->ub8; tp.umax = b->umax; tp.bins = reinterpret_cast<unsigned char *>(b->bins); tp.bias = (unsigned)f.la;
+            tp.ub8 = b->ub8; tp.umax = b->umax; tp.bins = reinterpret_cast<unsigned char *>(b->bins); tp.bias = (unsigned)f.la; tp.qblk0 = 0;
             tp.clk = nullptr;
 #ifdef QMANN_TC_TRACE
             static unsigned long long *clk_host_q = nullptr;
@@ -2134,13 +2153,43 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
             { unsigned long long *dp = nullptr; BCUDA(cudaHostGetDevicePointer((void **)&dp, clk_host_q, 0)); tp.clk = dp; }
             g_tcs_clk = clk_host_q;
 #endif
-            const size_t smem = (size_t)(TCS_NY + 3 * TQ_NP) * TCS_TILE + 2048;
             static bool attr_done = false;
-            if (!attr_done) { BCUDA(cudaFuncSetAttribute(k_big_scores_tq, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_optin)); attr_done = true; }
+            if (!attr_done) {
+                BCUDA(cudaFuncSetAttribute(k_big_scores_tq<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_optin));
+                BCUDA(cudaFuncSetAttribute(k_big_scores_tq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_optin));
+                BCUDA(cudaFuncSetAttribute(k_big_hist_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)HL_WARPS * 256 * 32 * 2)));
+                attr_done = true;
+            }
             const unsigned long long tiles = (b->S_local + 127) / 128;
             const unsigned gx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(tiles, (unsigned long long)b->sm_count));
-            k_big_scores_tq<<<dim3(gx, (Q + TQ_QB - 1) / TQ_QB), TCS_WARPS * 32, smem, st>>>(tp);
-            count_launch();
+            const unsigned nblk = (Q + TQ_QB - 1) / TQ_QB;
+            // Opt-in (QMANN_BIGMEM_OVERLAP=1: shards of >= 2^18 slots, 2: always): one scorer launch per query block, the histogram of
+            // block b on a second stream under the scorer of block b + 1; the scorer gives up one plane stage (145 KB) so that a 4-warp
+            // histogram CTA (64 KB) fits on the same SM.  Measured at Q = 1024 on one GPU: 1.77 ms per hop against 1.63 ms for the
+            // two kernels back to back -- both live on the shared-memory pipe (plane construction + operand reads, counter
+            // load/stores), so running them together only slows the scorer.  Kept for the record and covered by the tests.
+            const bool ovl = b->s2 && nblk >= 2 && b->bin8 && b->NB <= 256 && (b->overlap >= 2 || (b->overlap == 1 && b->S_local >= (1ull << 18)));
+            if (ovl) {
+                const size_t smem = (size_t)(TCS_NY + 3 * 2) * TCS_TILE + 2048, hl_smem = (size_t)4 * 256 * 32 * 2;
+                for (unsigned blk = 0; blk < nblk; blk++) {
+                    tp.qblk0 = blk;
+                    k_big_scores_tq<2><<<dim3(gx, 1), TCS_WARPS * 32, smem, st>>>(tp);
+                    count_launch();
+                    BCUDA(cudaEventRecord(b->ev_blk, st));
+                    BCUDA(cudaStreamWaitEvent(b->s2, b->ev_blk, 0));
+                    const unsigned qb0 = blk * TQ_QB, qn = std::min(TQ_QB, Q - qb0);
+                    k_big_hist_lanes<<<3 * b->sm_count, 4 * 32, hl_smem, b->s2>>>(reinterpret_cast<const unsigned char *>(b->bins) + (size_t)qb0 * b->S_local, b->S_local, qn,
+                                                                                 b->NB, 16384u, dev_hist + (size_t)qb0 * b->NB);
+                    count_launch();
+                }
+                BCUDA(cudaEventRecord(b->ev_join, b->s2));
+                BCUDA(cudaStreamWaitEvent(st, b->ev_join, 0));
+                hist_done = true;
+            } else {
+                const size_t smem = (size_t)(TCS_NY + 3 * 3) * TCS_TILE + 2048;
+                k_big_scores_tq<3><<<dim3(gx, nblk), TCS_WARPS * 32, smem, st>>>(tp);
+                count_launch();
+            }
             BCUDA(cudaPeekAtLastError());
             rc = QMANN_OK;
         }

@@ -114,6 +114,13 @@ def test_bigmem_fast_scorer_equals_per_product(d, S, Q, sigma, plant, qmann, syn
     np.testing.assert_array_equal(atom["hist"], slow["hist"], err_msg="k_big_hist")
     np.testing.assert_array_equal(atom["pred"], slow["pred"])
     monkeypatch.delenv("QMANN_BIGMEM_HIST_LANES")
+    if Q > 128:
+        # several query blocks: one scorer launch per block, the histogram of a block on a second stream under the next scorer
+        monkeypatch.setenv("QMANN_BIGMEM_OVERLAP", "2")
+        ovl = _run(qmann, cfg, w, M8, C8, u0)
+        for k in ("hist", "o", "u", "pred"):
+            np.testing.assert_array_equal(ovl[k], slow[k], err_msg=f"overlapped histogram: {k}")
+        monkeypatch.delenv("QMANN_BIGMEM_OVERLAP")
     # d <= 256 took k_big_scores_tq above (queries in tensor memory, 128 per pass); now k_big_scores_tc + k_big_hist
     monkeypatch.setenv("QMANN_BIGMEM_TQ", "0")
     tcs = _run(qmann, cfg, w, M8, C8, u0)
@@ -207,19 +214,29 @@ def test_bigmem_nccl_two_ranks(qmann):
     assert "BIGMEM_NCCL_OK" in r.stdout
 
 
-@pytest.mark.parametrize("mode,d,Q", [(2, 256, 70), (2, 64, 3), (3, 64, 5)])
-def test_bigmem_one_call_forward_equals_phase_api(mode, d, Q, qmann, synth):
+@pytest.mark.parametrize("mode,d,Q", [(2, 256, 70), (2, 64, 3), (3, 64, 5), (2, 256, 300)])
+def test_bigmem_one_call_forward_equals_phase_api(mode, d, Q, qmann, synth, monkeypatch):
     """qmann_bigmem_forward_sharded on a single shard (no communicator): the whole forward as one C call, captured into a CUDA graph
     on a side stream and replayed, and un-captured on the default stream -- same predictions and controller state as the phase API."""
     import torch
     cfg = synth.ModelConfig(V=40, d=d, S_max=64, V_dict=20, mode=mode, iwl=5 if mode == 2 else 3)
     w = synth.make_weights(cfg, 8, sigma=0.5)
     M8, C8, u0 = _random_memory(cfg, 3001, Q, 1234 + d, sigma=0.6 if mode == 2 else 0.3, plant_scale=3.0 if mode == 2 else 1.0)
+    if Q > 128:
+        # several query blocks: the per-block launches with the histogram on a second stream (forced: the shard is small), whose
+        # fork / join must also survive the graph capture
+        monkeypatch.setenv("QMANN_BIGMEM_OVERLAP", "0")
+        plain = qmann.lib.BigMemory(cfg, w, M8, C8, M8.shape[1], 0, Q_max=Q).forward(torch.from_numpy(u0).cuda())
+        torch.cuda.synchronize()
+        pred_plain = plain["pred"].clone()
+        monkeypatch.setenv("QMANN_BIGMEM_OVERLAP", "2")
     mem = qmann.lib.BigMemory(cfg, w, M8, C8, M8.shape[1], 0, Q_max=Q)
     u0d = torch.from_numpy(u0).cuda()
     ref = mem.forward(u0d)
     torch.cuda.synchronize()
     pred_ref, u_ref = ref["pred"].clone(), ref["u_final"].clone()
+    if Q > 128:
+        assert torch.equal(pred_ref, pred_plain), "overlapped histogram differs from the single-stream hop"
     side = torch.cuda.Stream()
     u0b = u0d.clone()
     for rep in range(3):                       # capture + two replays; then another input buffer forces a re-capture
