@@ -210,7 +210,13 @@ def reference_gpu_rate(synth, cfg, w, S, sample=2000, reps=2):
 C5_S, C5_D, C5_V = 1 << 20, 256, 64
 
 
-def c5_config(synth, mode=2):
+C5_MODE = 2          # --c5-attention hamming: 3 (the reference's approximate Hamming scorer; per-element kernel k_big_scores<3>)
+
+
+def c5_config(synth, mode=None):
+    mode = C5_MODE if mode is None else mode
+    if mode == 3:
+        return synth.ModelConfig(V=C5_V, d=C5_D, S_max=64, V_dict=32, mode=3, iwl=3)
     return synth.ModelConfig(V=C5_V, d=C5_D, S_max=64, V_dict=32, mode=mode)
 
 
@@ -494,7 +500,7 @@ def _bigmem_measure(args, torch, qlib, synth, cfg, weights, mem, u0, Q, W, K, ra
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-            "config": {"workload": f"C5: one pre-embedded memory of 2^20 slots, d=256, 3 hops, fixed-point dot attention, {Q} queries per step "
+            "config": {"workload": f"C5: one pre-embedded memory of 2^20 slots, d=256, 3 hops, {'Hamming (approximate)' if C5_MODE == 3 else 'fixed-point dot'} attention, {Q} queries per step "
                                    "(a story = one query against the whole memory)",
                        "memory": "int8 codes M_h, C_h per hop (1.61 GB), N(0,0.1)/N(0,0.5) quantised in the EN_MQ formats, resident in HBM",
                        "l2": f"{n_loc * cfg.d / 1e6:.0f} MB of M per hop and rank; three different hops' memories are streamed per step "
@@ -506,7 +512,7 @@ def _bigmem_measure(args, torch, qlib, synth, cfg, weights, mem, u0, Q, W, K, ra
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ((ncu_traffic("k_big_scores_fast") or {}).get("dram_bytes_per_launch") if (world == 1 and Q == 1) else
                                      (ncu_traffic("k_big_scores_tq") or {}).get("dram_bytes_per_launch") if (world == 1 and Q == 64) else None),
-                         "kernel": "k_big_scores_fast" if Q < 4 else ("k_big_scores_mma" if os.environ.get("QMANN_BIGMEM_TC") == "0" else
+                         "kernel": "k_big_scores<3> (per element)" if C5_MODE == 3 else "k_big_scores_fast" if Q < 4 else ("k_big_scores_mma" if os.environ.get("QMANN_BIGMEM_TC") == "0" else
                                                                       ("k_big_scores_tc" if os.environ.get("QMANN_BIGMEM_TQ") == "0" else "k_big_scores_tq")),
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
                          "algorithmic_bytes_per_launch": bytes_launch, "launch_ms": k_scores_ms,
@@ -619,8 +625,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
     ap.add_argument("--stories", type=int, default=0, help="C1-C4: stories per GPU and step (default: the workload's own count); BASELINE configs[3] sweeps 2^10 .. 2^20")
+    ap.add_argument("--c5-attention", default="dot", choices=["dot", "hamming"], help="C5: attention mode 2 (default) or 3")
     ap.add_argument("--quick", action="store_true", help="headline only: no sensitivity / e2e_ids / c5 / reference_gpu sections (profiling runs)")
     args = ap.parse_args()
+    global C5_MODE
+    C5_MODE = 3 if args.c5_attention == "hamming" else 2
     if args.impl == "reference":
         return run_reference(args)
     if args.impl == "reference_gpu":

@@ -68,14 +68,17 @@ struct HopFmt {
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_big_prep_query(const signed char *__restrict__ u, int fu, unsigned Q, unsigned d, int mode, HopFmt f,
                                                         int *__restrict__ ub, unsigned *__restrict__ av, unsigned *__restrict__ sv,
-                                                        signed char *__restrict__ ub8, unsigned *__restrict__ umax)
+                                                        signed char *__restrict__ ub8, unsigned *__restrict__ umax, int *__restrict__ u9,
+                                                        unsigned *__restrict__ quirk, int sh_u)
 {
-    // one CTA per query; ub8/umax feed k_big_scores_fast (|Q_bin(u)| <= lb <= 127 fits a byte)
+    // one CTA per query; ub8/umax feed k_big_scores_fast (|Q_bin(u)| <= lb <= 127 fits a byte); mode 3 also writes the nine-bit
+    // operand U9 = sat9(code << sh_u) of the fast Hamming form (see k_big_scores) and flags a query that holds the -2^iwl value
     __shared__ unsigned s_max;
     const unsigned q = blockIdx.x;
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
     unsigned mx = 0;
+    int qk = 0;
     for (unsigned t = threadIdx.x; t < d; t += blockDim.x) {
         const size_t i = (size_t)q * d + t;
         const int c = (int)u[i];
@@ -88,12 +91,20 @@ __global__ void __launch_bounds__(256) k_big_prep_query(const signed char *__res
             appx_encode(c, fu, f.ia, s_, m_);
             av[i] = m_;
             sv[i] = s_;
+            if (sh_u >= 0) {
+                const int tu = c << sh_u;
+                qk |= (tu == -256) ? 1 : 0;
+                u9[i] = max(-255, min(tu, 255));
+            }
         }
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
     if ((threadIdx.x & 31) == 0) atomicMax(&s_max, mx);
-    __syncthreads();
-    if (threadIdx.x == 0) umax[q] = s_max;
+    const int any_qk = __syncthreads_or(qk);
+    if (threadIdx.x == 0) {
+        umax[q] = s_max;
+        if (mode == 3) quirk[q] = any_qk ? 1u : 0u;
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -110,6 +121,9 @@ struct ScoreParams {
     int const_scale;
     const int *ub;                  // [Q][d]
     const unsigned *av, *sv;        // [Q][d] (mode 3)
+    const int *u9;                  // [Q][d] nine-bit operands (mode 3, fast form)
+    const unsigned *quirk;          // [Q] 1: the query holds the -2^iwl value (literal path for its block)
+    int nine, sh_m;                 // fast form usable (both shifts in 0..8), memory-side shift
     void *bins;                     // [Q][S_local] score bin = code + bias (uint8 in mode 2, uint16 in mode 3)
     int bin8;
     unsigned bias;                  // la (mode 2) or 127*d (mode 3)
@@ -138,10 +152,22 @@ __global__ void __launch_bounds__(256) k_big_scores(const ScoreParams p)
     unsigned *svs = avs + (size_t)QB * d;
     const size_t qbytes = (size_t)QB * d * 4 * (MODE == 3 ? 3 : 1);
     unsigned char *tile = sm + qbytes + (size_t)wid * 32 * rs;
+    // Mode 3 in nine bits (the form of the batched forward, qmann_fast.cuh): the reference compares 31-bit magnitudes
+    // |x| * 2^(31-iwl) (layer_cuda.cu:384-428) and keeps bits 30..24 of their difference or sum; every magnitude is a multiple of
+    // 2^23 or the saturated 0x7FFFFFFF, so the element is exact on A = sat9(code << sh) in [-255, 255]:  w = |A_m - A_u|,
+    // e = 127 - ((w >> 1) & 127), negative iff the signs differ and w < 256.  ~9 instructions per (slot, query, dim) instead of ~35.
+    // A query holding the -2^iwl value sends its block down the literal path.
+    bool nine = false;
+    if (MODE == 3 && p.nine) {
+        int qk = 0;
+        for (unsigned q = threadIdx.x; q < nq; q += blockDim.x) qk |= (int)p.quirk[q0 + q];
+        nine = !__syncthreads_or(qk);
+    }
+    const int sh_m = p.sh_m;
     for (unsigned i = threadIdx.x; i < QB * d; i += blockDim.x) {
         const unsigned q = i / d, t = i % d;
         const bool ok = q < nq;
-        ubs[i] = ok ? p.ub[(size_t)(q0 + q) * d + t] : 0;
+        ubs[i] = ok ? ((MODE == 3 && nine) ? p.u9[(size_t)(q0 + q) * d + t] : p.ub[(size_t)(q0 + q) * d + t]) : 0;
         if (MODE == 3) {
             avs[i] = ok ? p.av[(size_t)(q0 + q) * d + t] : 0u;
             svs[i] = ok ? p.sv[(size_t)(q0 + q) * d + t] : 0u;
@@ -178,7 +204,13 @@ __global__ void __launch_bounds__(256) k_big_scores(const ScoreParams p)
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const int code = sx8(ww[j >> 2], j & 3);
-                if (MODE == 3) {
+                if (MODE == 3 && nine) {
+                    int t = code << sh_m;
+                    t = (t == -256) ? 0 : max(-255, min(t, 255));          // -2^iwl encodes to 0 (it keeps its sign: smb); a caller's -128 too
+                    m[j] = t;
+                    am[j] = 0;
+                    smb |= (code < 0 ? 1u : 0u) << j;
+                } else if (MODE == 3) {
                     unsigned s_, m_;
                     appx_encode(code, f.fw, f.ia, s_, m_);
                     am[j] = m_;
@@ -192,7 +224,21 @@ __global__ void __launch_bounds__(256) k_big_scores(const ScoreParams p)
 #pragma unroll
             for (int q = 0; q < QB; q++) {
                 int part = 0;
-                if (MODE == 3) {
+                if (MODE == 3 && nine) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        const int4 u4 = *reinterpret_cast<const int4 *>(ubs + (size_t)q * d + c * 16 + j4 * 4);
+                        const int uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int j = j4 * 4 + k;
+                            const int w9 = (int)__sad(m[j], uu[k], 0u);
+                            const int e = ~(w9 >> 1) & 0x7F;
+                            const bool neg = (((int)(((smb >> j) & 1u) << 31) ^ uu[k]) < 0) && (w9 < 256);
+                            part += neg ? -e : e;
+                        }
+                    }
+                } else if (MODE == 3) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; j4++) {
                         const uint4 a4 = *reinterpret_cast<const uint4 *>(avs + (size_t)q * d + c * 16 + j4 * 4);
@@ -1821,6 +1867,9 @@ struct qmann_bigmem {
     unsigned Q_max, Q, NB, bias;
     HopFmt f[MAXH];
     signed char *dev_H[MAXH];
+    int *u9;                    // mode 3: nine-bit query operands, per-query quirk flags
+    unsigned *quirk;
+    bool nine_on;
     unsigned char *dev_hmax[MAXH];      // row maxima of dev_H (k_big_update_fast)
     bool fast_update;
     const float *dev_W;
@@ -2007,6 +2056,8 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
     BCUDA_B(cudaMalloc((void **)&b->ub, Qd * 4));
     BCUDA_B(cudaMalloc((void **)&b->av, Qd * 4));
     BCUDA_B(cudaMalloc((void **)&b->sv, Qd * 4));
+    BCUDA_B(cudaMalloc((void **)&b->u9, Qd * 4));
+    BCUDA_B(cudaMalloc((void **)&b->quirk, (size_t)Q_max * 4));
     BCUDA_B(cudaMalloc((void **)&b->ub8, Qd));
     BCUDA_B(cudaMalloc((void **)&b->umax, (size_t)Q_max * 4));
     {
@@ -2038,6 +2089,7 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
     const char *env_fast = getenv("QMANN_BIGMEM_FAST");
     const bool want_fast = c.mode == 2 && c.frac_bin == 2 && (c16 & (c16 - 1)) == 0 && c16 <= 32 && S_local > 0 &&
                            !(env_fast && atoi(env_fast) == 0);
+    b->nine_on = !(env_fast && atoi(env_fast) == 0);
     b->fast_update = c.mode == 2 && c.frac_bin == 2 && c.d % 16 == 0 && c.lin_map && !(env_fast && atoi(env_fast) == 0);
     if (want_fast) {
         unsigned *dev_flag = nullptr;
@@ -2096,7 +2148,7 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
 void qmann_bigmem_destroy(qmann_bigmem *b)
 {
     if (!b) return;
-    cudaFree(b->u_a); cudaFree(b->u_b); cudaFree(b->ub); cudaFree(b->av); cudaFree(b->sv); cudaFree(b->bins);
+    cudaFree(b->u_a); cudaFree(b->u_b); cudaFree(b->ub); cudaFree(b->av); cudaFree(b->sv); cudaFree(b->u9); cudaFree(b->quirk); cudaFree(b->bins);
     cudaFree(b->ub8); cudaFree(b->umax); cudaFree(b->bfrag); cudaFree(b->bplanes);
     cudaFree(b->xhist); cudaFree(b->xpartial);
     if (b->gexec) cudaGraphExecDestroy(b->gexec);
@@ -2129,13 +2181,17 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned Q = b->Q, d = b->cfg.d;
     const HopFmt &f = b->f[h];
-    k_big_prep_query<<<Q, 256, 0, st>>>(b->u_a, b->fu, Q, d, (int)b->cfg.mode, f, b->ub, b->av, b->sv, b->ub8, b->umax);
+    // mode 3, nine-bit form: A = sat9(code << (8 - iwl_att - frac)); usable when both shifts are in 0..8 (QMANN_BIGMEM_FAST=0: literal)
+    const int sh_m = 8 - f.ia - f.fw, sh_u = 8 - f.ia - b->fu;
+    const bool nine = b->cfg.mode == 3 && b->nine_on && sh_m >= 0 && sh_m <= 8 && sh_u >= 0 && sh_u <= 8;
+    k_big_prep_query<<<Q, 256, 0, st>>>(b->u_a, b->fu, Q, d, (int)b->cfg.mode, f, b->ub, b->av, b->sv, b->ub8, b->umax, b->u9, b->quirk, nine ? sh_u : -1);
     count_launch();
     BCUDA(cudaMemsetAsync(dev_hist, 0, (size_t)Q * b->NB * 4, st));
     if (b->S_local) {
         ScoreParams sp;
         sp.M = b->M[h]; sp.S_local = b->S_local; sp.d = d; sp.Q = Q; sp.f = f; sp.const_scale = b->cfg.const_scale;
         sp.ub = b->ub; sp.av = b->av; sp.sv = b->sv; sp.bins = b->bins; sp.bin8 = b->bin8;
+        sp.u9 = b->u9; sp.quirk = b->quirk; sp.nine = nine ? 1 : 0; sp.sh_m = sh_m;
         sp.bias = (b->cfg.mode == 3) ? b->bias : (unsigned)f.la;
         int rc;
         const bool prof = b->profile && b->pused + 2 <= 2 * MAXH;
@@ -2245,7 +2301,7 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
             fp.ub8 = b->ub8; fp.umax = b->umax; fp.bins = b->bins; fp.bin8 = b->bin8; fp.bias = (unsigned)f.la;
             rc = dispatch_scores_fast(b, fp, st);
         }
-        else if (b->cfg.mode == 3) rc = (Q >= 4) ? launch_scores<3, 4>(b, sp, st) : launch_scores<3, 1>(b, sp, st);
+        else if (b->cfg.mode == 3) rc = (Q >= 8) ? launch_scores<3, 8>(b, sp, st) : (Q >= 4 ? launch_scores<3, 4>(b, sp, st) : launch_scores<3, 1>(b, sp, st));
         else rc = (Q >= 16) ? launch_scores<2, 16>(b, sp, st) : (Q >= 4 ? launch_scores<2, 4>(b, sp, st) : launch_scores<2, 1>(b, sp, st));
         if (rc) return rc;
         if (prof) { BCUDA(cudaEventRecord(b->pev[b->pused + 1], st)); b->pused += 2; }

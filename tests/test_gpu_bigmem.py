@@ -137,6 +137,41 @@ def test_bigmem_fast_scorer_equals_per_product(d, S, Q, sigma, plant, qmann, syn
         np.testing.assert_array_equal(packed[k], slow[k], err_msg=k)
 
 
+@pytest.mark.parametrize("iwl,d,S,Q", [(3, 64, 1500, 11), (2, 32, 700, 8), (3, 256, 640, 19), (4, 48, 900, 5)])
+def test_bigmem_hamming_nine_bit_equals_literal(iwl, d, S, Q, qmann, synth, qmo, monkeypatch):
+    """Mode 3 on the large memory: the nine-bit form of the approximate Hamming element (w = |A_m - A_u| on sat9(code << shift)) against
+    the literal 31-bit sign-magnitude form (QMANN_BIGMEM_FAST=0) and the oracle.  The memory holds the extremes (+-127, the codes that
+    saturate the nine-bit operand, the -2^iwl value on the memory side); one query of the LAST block holds the -2^iwl value, which
+    sends that block down the literal path while the first block stays on the fast one."""
+    import qmo_bigmem as qb
+    cfg = synth.ModelConfig(V=40, d=d, S_max=64, V_dict=20, mode=3, iwl=iwl)
+    w = synth.make_weights(cfg, 5, sigma=0.5)
+    M8, C8, u0 = _random_memory(cfg, S, Q, 4000 + d + Q, sigma=0.3, plant_scale=1.0)
+    f = cfg.formats()
+    rng = np.random.default_rng(7)
+    for h in range(cfg.H):
+        sh_m = 8 - f["iwl_att"][h] - f["frac_w"][h]
+        M8[h, 3, :] = 127
+        M8[h, 4, :] = -127
+        M8[h, 5, ::2] = -128
+        if 0 <= sh_m <= 7:
+            M8[h, 6, :] = -(256 >> sh_m) if (256 >> sh_m) <= 127 else -127      # code << sh_m == -256: the value that encodes to 0
+            M8[h, 7, :] = (256 >> sh_m) - 1 if (256 >> sh_m) <= 128 else 127
+        M8[h, 8] = rng.integers(-127, 128, d)
+    sh_u = 8 - f["iwl_att"][0] - f["frac_w"][0]
+    if 0 <= sh_u <= 7 and (256 >> sh_u) <= 127:
+        u0[Q - 1, 1] = -(256 >> sh_u)
+    u0[0, :4] = [127, -127, 0, 1]
+    fast = _run(qmann, cfg, w, M8, C8, u0)
+    if d <= 64:                                 # (the oracle recovers the raw sums from the score values: not when a sum saturates, d = 256)
+        ref = qb.forward(cfg, w, M8, C8, u0)
+        np.testing.assert_array_equal(fast["hist"].astype(np.int64), ref["hist"].astype(np.int64), err_msg="nine-bit form vs oracle")
+    monkeypatch.setenv("QMANN_BIGMEM_FAST", "0")
+    lit = _run(qmann, cfg, w, M8, C8, u0)
+    for k in ("hist", "o", "g", "u", "pred"):
+        np.testing.assert_array_equal(fast[k], lit[k], err_msg=f"nine-bit form vs literal kernel: {k}")
+
+
 @pytest.mark.parametrize("mode", [2, 3])
 def test_bigmem_shards_agree(mode, qmann, synth):
     cfg = synth.ModelConfig(V=40, d=64, S_max=64, V_dict=20, mode=mode, iwl=5 if mode == 2 else 3)
