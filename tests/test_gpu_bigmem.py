@@ -137,9 +137,10 @@ def test_bigmem_fast_scorer_equals_per_product(d, S, Q, sigma, plant, qmann, syn
         np.testing.assert_array_equal(packed[k], slow[k], err_msg=k)
 
 
-@pytest.mark.parametrize("iwl,d,S,Q", [(3, 64, 1500, 11), (2, 32, 700, 8), (3, 256, 640, 19), (4, 48, 900, 5)])
+@pytest.mark.parametrize("iwl,d,S,Q", [(3, 64, 1500, 21), (2, 32, 700, 17), (3, 256, 640, 19), (4, 48, 900, 5), (3, 64, 333, 7)])
 def test_bigmem_hamming_nine_bit_equals_literal(iwl, d, S, Q, qmann, synth, qmo, monkeypatch):
-    """Mode 3 on the large memory: the nine-bit form of the approximate Hamming element (w = |A_m - A_u| on sat9(code << shift)) against
+    """Mode 3 on the large memory: the packed-byte scorer k_big_scores_ham (four elements per instruction) and the scalar nine-bit form
+    (QMANN_BIGMEM_HAM=0) of the approximate Hamming element (w = |A_m - A_u| on sat9(code << shift)) against
     the literal 31-bit sign-magnitude form (QMANN_BIGMEM_FAST=0) and the oracle.  The memory holds the extremes (+-127, the codes that
     saturate the nine-bit operand, the -2^iwl value on the memory side); one query of the LAST block holds the -2^iwl value, which
     sends that block down the literal path while the first block stays on the fast one."""
@@ -166,10 +167,13 @@ def test_bigmem_hamming_nine_bit_equals_literal(iwl, d, S, Q, qmann, synth, qmo,
     if d <= 64:                                 # (the oracle recovers the raw sums from the score values: not when a sum saturates, d = 256)
         ref = qb.forward(cfg, w, M8, C8, u0)
         np.testing.assert_array_equal(fast["hist"].astype(np.int64), ref["hist"].astype(np.int64), err_msg="nine-bit form vs oracle")
+    monkeypatch.setenv("QMANN_BIGMEM_HAM", "0")
+    nine = _run(qmann, cfg, w, M8, C8, u0)
     monkeypatch.setenv("QMANN_BIGMEM_FAST", "0")
     lit = _run(qmann, cfg, w, M8, C8, u0)
     for k in ("hist", "o", "g", "u", "pred"):
-        np.testing.assert_array_equal(fast[k], lit[k], err_msg=f"nine-bit form vs literal kernel: {k}")
+        np.testing.assert_array_equal(fast[k], lit[k], err_msg=f"packed-byte scorer vs literal kernel: {k}")
+        np.testing.assert_array_equal(nine[k], lit[k], err_msg=f"nine-bit form vs literal kernel: {k}")
 
 
 @pytest.mark.parametrize("mode", [2, 3])

@@ -119,6 +119,44 @@ def test_hamming_element_in_nine_bits():
         np.testing.assert_array_equal(got, k["out"][ci].astype(np.float64), err_msg=str((ia, fM, fu)))
 
 
+def test_hamming_element_on_packed_bytes():
+    """k_big_scores_ham: the nine-bit element on magnitude bytes.  With a = |A_m|, b = |A_u| in 0..255 and the two sign flags,
+    e + 127 = 254 - (|a - b| >> 1) when the signs agree, and with m = (a + b) >> 1 (a byte: the halving add) it is m for m < 128 and
+    382 - m otherwise when they differ -- every step a per-byte operation without carries between bytes.  Also the per-byte
+    encoder a = sat8(|code| << sh) with the -2^iwl value mapped to 0.  All 8-bit code pairs, shifts 0..4."""
+    codes = np.arange(-128, 128, dtype=np.int64)
+    for sh_m in range(0, 5):
+        for sh_u in range(0, 5):
+            def enc9(n, sh):
+                t = n * (1 << sh)
+                return np.where(t == -256, 0, np.clip(t, -255, 255))
+            A, U = enc9(codes, sh_m), enc9(codes, sh_u)
+            w = np.abs(A[:, None] - U[None, :])
+            e = (~(w >> 1)) & 0x7F
+            neg = ((codes[:, None] ^ U[None, :]) < 0) & (w < 256)
+            want = np.where(neg, -e, e)
+            # byte encoder as the kernel does it on four packed bytes
+            def enc_bytes(n, sh):
+                mag = np.abs(n)                                            # <= 128
+                thr = 256 >> sh
+                ov = ((mag + (128 - thr)) & 0x80) != 0 if thr <= 128 else np.zeros_like(mag, bool)
+                a = np.where(ov, 255, (mag << sh) & 0xFF)
+                a = np.where((n < 0) & (mag == thr), 0, a)                 # code << sh == -256 encodes to 0, the sign stays
+                return a
+            a, b = enc_bytes(codes, sh_m), enc_bytes(codes, sh_u)
+            assert np.array_equal(a, np.abs(A)) and np.array_equal(b, np.abs(U))
+            sm, su = codes < 0, U < 0                                      # query sign: of the nine-bit value (0 is positive)
+            aa, bb = a[:, None], b[None, :]
+            xs = 254 - (np.abs(aa - bb) >> 1)
+            m = (aa & bb) + (((aa ^ bb) & 0xFE) >> 1)
+            assert np.array_equal(m, (aa + bb) >> 1)
+            mask = np.where(m & 0x80, 0xFF, 0)
+            xd = (m ^ mask) + (mask & 0x7F)
+            assert xd.max() <= 254 and xs.min() >= 0
+            x = np.where(sm[:, None] ^ su[None, :], xd, xs)
+            np.testing.assert_array_equal(x - 127, want, err_msg=str((sh_m, sh_u)))
+
+
 def test_answer_prefilter_bound():
     """k_forward_fast's answer prefilter: with W8 = rint(W/s), s = max|W|/127 and u = n/2^fu, the fp32 logit computed in
     the reference's order satisfies |z * 2^fu / s - D| <= |n|_1 * (1/2 + 127 * gamma_{d+1}) for D = W8 . n, so the row of
