@@ -512,7 +512,7 @@ def _bigmem_measure(args, torch, qlib, synth, cfg, weights, mem, u0, Q, W, K, ra
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ((ncu_traffic("k_big_scores_fast") or {}).get("dram_bytes_per_launch") if (world == 1 and Q == 1) else
                                      (ncu_traffic("k_big_scores_tq") or {}).get("dram_bytes_per_launch") if (world == 1 and Q == 64) else None),
-                         "kernel": "k_big_scores<3> (per element)" if C5_MODE == 3 else "k_big_scores_fast" if Q < 4 else ("k_big_scores_mma" if os.environ.get("QMANN_BIGMEM_TC") == "0" else
+                         "kernel": "k_big_scores_ham (packed bytes)" if C5_MODE == 3 else "k_big_scores_fast" if Q < 4 else ("k_big_scores_mma" if os.environ.get("QMANN_BIGMEM_TC") == "0" else
                                                                       ("k_big_scores_tc" if os.environ.get("QMANN_BIGMEM_TQ") == "0" else "k_big_scores_tq")),
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
                          "algorithmic_bytes_per_launch": bytes_launch, "launch_ms": k_scores_ms,

@@ -330,7 +330,8 @@ __device__ __forceinline__ unsigned ham_word(unsigned a, unsigned sa, unsigned b
     const unsigned sd = sa ^ sb;
     const unsigned xs = 0xFEFEFEFEu - ((__vabsdiffu4(a, b) >> 1) & 0x7F7F7F7Fu);
     const unsigned m = (a & b) + (((a ^ b) & 0xFEFEFEFEu) >> 1);
-    const unsigned mk = ((m >> 7) & 0x01010101u) * 0xFFu;
+    unsigned mk;
+    asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(mk) : "r"(m));                  // 0xFF in the bytes with m >= 128
     const unsigned xd = (m ^ mk) + (mk & 0x7F7F7F7Fu);
     return (xd & sd) | (xs & ~sd);
 }
