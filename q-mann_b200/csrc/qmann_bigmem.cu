@@ -2019,7 +2019,7 @@ struct qmann_bigmem {
     cudaStream_t s2;            // histogram of query block b under the scorer of block b + 1 (qmann_bigmem_hop_scores)
     cudaEvent_t ev_blk, ev_join;
     int overlap;                // QMANN_BIGMEM_OVERLAP: 0 off (default), 1 large shards, 2 always
-    bool tq_ok;                 // k_big_scores_tq: queries in tensor memory, 128 per pass, histogram fused (d <= 256, byte bins)
+    bool tq_ok, tq_wide;        // tq_wide (QMANN_BIGMEM_TQ_WIDE=1): always one CTA per SM and query block                 // k_big_scores_tq: queries in tensor memory, 128 per pass, histogram fused (d <= 256, byte bins)
     CUtensorMap tmY[MAXH];
     // k_big_scores_fast inputs per hop: Y = Q_att(M) (== M when the re-quantisation is the identity), row maxima
     const signed char *Y[MAXH];
@@ -2269,6 +2269,7 @@ int qmann_bigmem_create(qmann_bigmem **out, const qmann_config *cfg, const qmann
         b->tc_ok = ok;
         const char *env_tq = getenv("QMANN_BIGMEM_TQ");
         const size_t need_tq = (size_t)(TCS_NY + 3 * 3) * TCS_TILE + 2048;
+        { const char *env_w = getenv("QMANN_BIGMEM_TQ_WIDE"); b->tq_wide = env_w && atoi(env_w) != 0; }
         b->tq_ok = ok && c.d <= 256 && b->bin8 && c.mode == 2 && b->NB <= 256 && need_tq <= (size_t)b->smem_optin && !(env_tq && atoi(env_tq) == 0);
     }
     {
@@ -2357,8 +2358,15 @@ int qmann_bigmem_hop_scores(qmann_bigmem *b, uint32_t h, uint32_t *dev_hist, voi
                 attr_done = true;
             }
             const unsigned long long tiles = (b->S_local + 127) / 128;
-            const unsigned gx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(tiles, (unsigned long long)b->sm_count));
             const unsigned nblk = (Q + TQ_QB - 1) / TQ_QB;
+            // One CTA per SM at a time.  With several query blocks over a small shard (multi-GPU) a CTA per SM and block would see only
+            // a handful of tiles, and every CTA pays for writing its query planes into tensor memory and for filling the pipeline:
+            // use fewer, longer CTAs per block -- gx * nblk = waves * SMs with at least ~24 tiles per CTA where the work allows it.
+            unsigned gx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(tiles, (unsigned long long)b->sm_count));
+            if (nblk >= 2 && !b->tq_wide) {
+                const unsigned long long waves = std::max<unsigned long long>(1, std::min<unsigned long long>(nblk, tiles * nblk / ((unsigned long long)b->sm_count * 24)));
+                gx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(tiles, (unsigned long long)b->sm_count * waves / nblk));
+            }
             // Opt-in (QMANN_BIGMEM_OVERLAP=1: shards of >= 2^18 slots, 2: always): one scorer launch per query block, the histogram of
             // block b on a second stream under the scorer of block b + 1; the scorer gives up one plane stage (145 KB) so that a 4-warp
             // histogram CTA (64 KB) fits on the same SM.  Measured at Q = 1024 on one GPU: 1.77 ms per hop against 1.63 ms for the
