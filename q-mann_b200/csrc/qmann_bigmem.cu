@@ -1585,12 +1585,15 @@ __global__ void __launch_bounds__(HL_WARPS * 32, 1) k_big_hist_lanes(const unsig
         __syncwarp();
         unsigned *hq = hist + (size_t)q * NB;
         for (unsigned bin0 = 0; bin0 < NB; bin0 += 8) {
-            unsigned c[8], mine = 0u;
+            unsigned c[8], mine = 0u, any = 0u;
 #pragma unroll
             for (unsigned k = 0; k < 8; k++) {                  // cnt has 256 rows: bins NB .. 255 stay zero
                 c[k] = cl[(bin0 + k) * 32u];
-                cl[(bin0 + k) * 32u] = 0;
+                any |= c[k];
             }
+            if (!__any_sync(0xffffffffu, any != 0u)) continue;  // the scores of a query occupy a few dozen neighbouring bins
+#pragma unroll
+            for (unsigned k = 0; k < 8; k++) cl[(bin0 + k) * 32u] = 0;
 #pragma unroll
             for (unsigned k = 0; k < 8; k++) {
                 const unsigned t = __reduce_add_sync(0xffffffffu, c[k]);
