@@ -70,6 +70,7 @@ struct qmann_model {
     qmann_config cfg;
     int device;
     int sm_count;
+    unsigned compact_ctas_per_sm = 8;   // grid cap of k_compact in CTAs per SM (QMANN_COMPACT_CTAS_PER_SM)
     int max_smem = 0;
     unsigned char *dev_img = nullptr;
     signed char *dev_lut = nullptr;          // linear-map product tables (k_prep_lut), NULL when too large
@@ -346,6 +347,7 @@ static int model_build(qmann_model *m, const qmann_config *cfg, const qmann_weig
     cudaDeviceProp prop;
     QCUDA(cudaGetDeviceProperties(&prop, m->device));
     m->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("QMANN_COMPACT_CTAS_PER_SM")) m->compact_ctas_per_sm = (unsigned)std::min(64, std::max(1, atoi(e)));
 
     // ---- image layout ----
     unsigned LPR = 4;
@@ -779,7 +781,7 @@ static int forward_range(qmann_model *m, const qmann_batch *b, uint32_t first, u
             return cp;
         };
         auto launch_compact = [&](const CompactParams &cp, unsigned n_est) -> int {
-            const unsigned cblocks = std::max(1u, std::min<unsigned>((n_est + 7) / 8, (unsigned)m->sm_count * 8));
+            const unsigned cblocks = std::max(1u, std::min<unsigned>((n_est + 7) / 8, (unsigned)m->sm_count * m->compact_ctas_per_sm));
             if (vec4) k_compact<4><<<cblocks, 256, 0, st>>>(cp);
             else if (vec2) k_compact<2><<<cblocks, 256, 0, st>>>(cp);
             else           k_compact<1><<<cblocks, 256, 0, st>>>(cp);
