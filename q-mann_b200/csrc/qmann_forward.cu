@@ -177,6 +177,9 @@ int launch_story_t(const qmann_model *m, const FwdParams &p, bool dump, cudaStre
     const unsigned per_sm = (p.n_stories + (unsigned)m->sm_count - 1) / (unsigned)m->sm_count;
     unsigned nw = std::min(m->NW_fast, std::max(std::min(8u, m->NW_fast), (per_sm + 3) / 4 * 4));
     if (dump) nw = std::min(nw, 16u);
+    // 28 / 32 warps (64 registers each) exist for the packed record tier of the d <= 64 / dot-attention shape only (QMANN_FAST_WARPS=28 / 32)
+    constexpr bool HAS896 = SWAR && !DENSE && LPR == 4 && MODE == 2;
+    if (!HAS896) nw = std::min(nw, 24u);
     const unsigned smem = p.fl.tables_bytes + nw * p.fl.warp_bytes;
     const unsigned grid = (unsigned)m->sm_count;
 #define QM_LAUNCH(DUMP_, MAXT_)                                                                                              \
@@ -189,6 +192,8 @@ int launch_story_t(const qmann_model *m, const FwdParams &p, bool dump, cudaStre
         k_story<LPR, MODE, SWAR, DENSE, DUMP_, MAXT_><<<grid, nw * 32, smem, st>>>(p);                                        \
     } while (0)
     if (dump) QM_LAUNCH(true, 512);
+    else if (nw > 28) { if constexpr (HAS896) QM_LAUNCH(false, 1024); }
+    else if (nw > 24) { if constexpr (HAS896) QM_LAUNCH(false, 896); }
     else if (nw > 16) QM_LAUNCH(false, 768);
     else QM_LAUNCH(false, 512);
 #undef QM_LAUNCH
@@ -574,10 +579,10 @@ static int model_build(qmann_model *m, const qmann_config *cfg, const qmann_weig
         fl.warp_bytes = round_up(o2, 128);
         // entries are 16-bit offsets column * DP
         if ((size_t)(c.V + 1) * DP > 65535u) m->fast_ok = false;
-        unsigned cap = 24;
+        unsigned cap = 28;      // 28 measured best for the packed record tier (24: 0.302 ms, 28: 0.292, 32: 0.307 on C2; profiles/r02_story_warps_sweep.txt)
         if (const char *e = getenv("QMANN_FAST_WARPS")) cap = (unsigned)std::max(1, atoi(e));
         m->NW_fast = 0;
-        for (unsigned want : {24u, 22u, 20u, 18u, 16u, 14u, 12u, 10u, 8u, 6u, 4u, 2u, 1u}) {
+        for (unsigned want : {32u, 28u, 24u, 22u, 20u, 18u, 16u, 14u, 12u, 10u, 8u, 6u, 4u, 2u, 1u}) {
             if (want > cap) continue;
             if ((size_t)fl.tables_bytes + (size_t)want * fl.warp_bytes + 1024 <= (size_t)max_smem) { m->NW_fast = want; break; }
         }
